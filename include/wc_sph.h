@@ -1,0 +1,176 @@
+/*
+ * wc_sph.h -- C-ABI of the B200-native WaterCube SPH step.
+ *
+ * The reference has no plugin/FFI ABI: its boundary is the C++ class surface of
+ * core::Fluid (src/core/Fluid.h:32-59) and core::Sort (src/core/Sort.h:20-39), which
+ * drive five GLSL compute dispatches per frame (src/core/Fluid.cpp:342-354,
+ * src/core/Sort.cpp:254-267).  This header is the drop-in boundary for that path:
+ * plain pointers and sizes, an opaque handle, `int` status (0 = ok) plus
+ * wc_last_error().  The C++ facade (watercube_b200/csrc/core/Fluid.h, Sort.h, util.h)
+ * keeps the reference's method names on top of exactly these calls; INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.
+ *
+ * Threading: a handle is not thread-safe (the reference calls Fluid::update from the
+ * single Cinder main thread, src/WaterCubeApp.cpp:98).  All work of a handle is ordered
+ * on one CUDA stream.  There is NO CPU fallback: every call fails with WC_ERR_NO_DEVICE /
+ * WC_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef WC_SPH_H
+#define WC_SPH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WC_ABI_VERSION 1
+
+enum {
+    WC_OK = 0,
+    WC_ERR_INVALID = 1,   /* bad argument / call order */
+    WC_ERR_NO_DEVICE = 2, /* no CUDA device, or device ordinal out of range */
+    WC_ERR_CUDA = 3,      /* a CUDA runtime call or kernel failed; see wc_last_error() */
+    WC_ERR_CAPACITY = 4   /* particle count exceeds the handle's capacity */
+};
+
+/* wc_params.flags */
+enum {
+    WC_FLAG_DEBUG_OUTPUTS = 1, /* also store neighbour counts and total forces (parity runs) */
+    WC_FLAG_STAGE_TIMING = 2,  /* record CUDA events around every stage of wc_step */
+    WC_FLAG_SIMPLE_KERNELS = 4 /* use the simple thread-per-particle gather kernels
+                                  (cross-check for the warp-cooperative tiled ones) */
+};
+
+/* Stages of one step, in execution order (index into wc_stage_times). */
+enum {
+    WC_STAGE_HASH_COUNT = 0, /* count.comp (+ counter clear, Sort.cpp:255-256) */
+    WC_STAGE_SCAN = 1,       /* linearScan.comp (Sort.cpp:258-259) */
+    WC_STAGE_REORDER = 2,    /* reorder.comp, made stable (Sort.cpp:263-264) */
+    WC_STAGE_DENSITY = 3,    /* density.comp (Fluid.cpp:349) */
+    WC_STAGE_UPDATE = 4,     /* update.comp (Fluid.cpp:350) */
+    WC_NUM_STAGES = 5
+};
+
+/* 32-byte AoS particle: struct Particle, src/core/util.h:29-35 (GLSL mirror
+ * assets/fluid/density.comp:5-10).  This is the host-visible particle-buffer layout of
+ * util::getParticles / util::setParticles (src/core/util.cpp:42-63). */
+typedef struct wc_particle {
+    float position[3];
+    float density;
+    float velocity[3];
+    float pressure;
+} wc_particle;
+
+/* Setup-time parameters: Fluid's constructor defaults and fluent setters
+ * (src/core/Fluid.cpp:9-27, :31-84).  N, gridRes, size and radius are fixed at setup
+ * (Fluid::setup, Fluid.cpp:203-235). */
+typedef struct wc_params {
+    int32_t num_particles;  /* Fluid::numParticles(int), default 80000 */
+    int32_t capacity;       /* particle slots to allocate; 0 = num_particles */
+    int32_t grid_res;       /* Fluid::gridRes(int), default 21 */
+    float size;             /* Fluid::size(float), default 1 */
+    float particle_radius;  /* Fluid::particleRadius(float), default 0.01 */
+    float time_scale;       /* Fluid.cpp:24, default 0.012: dt = frame_dt * time_scale */
+    int32_t device;         /* CUDA device ordinal */
+    uint32_t flags;         /* WC_FLAG_* */
+    void* stream;           /* optional caller-owned cudaStream_t; NULL = library-owned */
+} wc_params;
+
+/* Per-step parameters: the fields the reference re-uploads as uniforms on every
+ * dispatch (GUI-mutable, src/core/Fluid.cpp:89-99, :276-285, :305-317). */
+typedef struct wc_step_params {
+    float viscosity_coefficient; /* default 200 */
+    float stiffness;             /* default 100 */
+    float rest_density;          /* default 500 */
+    float rest_pressure;         /* default 0 */
+    float gravity[3];            /* gravity_direction_ * gravity_strength_, default (0,-900,0) */
+    float mouse_origin[3];       /* "cameraPosition" uniform: mouse ray origin, box space */
+    float mouse_dir[3];          /* "mouseRayDirection" uniform */
+} wc_step_params;
+
+/* Constants derived in Fluid::setup (src/core/Fluid.cpp:206-216). */
+typedef struct wc_derived {
+    int32_t num_bins;
+    float bin_size;
+    float kernel_radius;
+    float particle_mass;
+    float poly6_const;
+    float spiky_const;
+    float visc_const;
+    float dist2_threshold; /* smallest fp32 x with sqrtf(x) >= kernel_radius */
+} wc_derived;
+
+/* Raw device pointers for zero-copy consumers (future CUDA-GL interop of
+ * Fluid::renderParticles, Fluid.cpp:389-406).  SoA float4: pos_rho = (x,y,z,density),
+ * vel_pres = (vx,vy,vz,pressure).  Index 0 = "buffer 1" (current state), 1 = "buffer 2"
+ * (cell-sorted input of the last step with density/pressure filled in). */
+typedef struct wc_device_view {
+    void* pos_rho[2];
+    void* vel_pres[2];
+    void* cell_ids;         /* uint32[num_particles], per INPUT particle of the last sort */
+    void* counts;           /* uint32[num_bins]      Sort::getCountBuffer  */
+    void* offsets;          /* uint32[num_bins + 1]  Sort::getOffsetBuffer (+ total sentinel) */
+    void* sorted;           /* uint32[num_particles] Sort::getSortedBuffer: sorted[dst] = src */
+    void* neighbour_counts; /* uint32[num_particles] (WC_FLAG_DEBUG_OUTPUTS) or NULL */
+    void* forces;           /* float4[num_particles] (WC_FLAG_DEBUG_OUTPUTS) or NULL */
+    void* stream;           /* the cudaStream_t all work is ordered on */
+    int32_t num_particles;
+    int32_t capacity;
+} wc_device_view;
+
+int wc_abi_version(void);
+const char* wc_last_error(void);
+
+/* Fluid::Fluid defaults (Fluid.cpp:9-27); mouse ray defaults to one that misses the box. */
+int wc_default_params(wc_params* p);
+int wc_default_step_params(wc_step_params* sp);
+/* Fluid::setup constants without touching a device (Fluid.cpp:206-216). */
+int wc_derive(const wc_params* p, wc_derived* d);
+
+/* Fluid::setup (Fluid.cpp:203-235) + Sort::prepareBuffers (Sort.cpp:67-94): allocate the
+ * two particle buffers, count/offset/sorted buffers and scratch on p->device. */
+typedef struct wc_handle wc_handle;
+int wc_create(const wc_params* p, wc_handle** out);
+int wc_destroy(wc_handle* h);
+int wc_get_derived(const wc_handle* h, wc_derived* d);
+
+/* util::setParticles (util.cpp:59-63) into buffer 1, n <= capacity; sets num_particles. */
+int wc_upload_particles(wc_handle* h, const wc_particle* host_aos, int32_t n);
+/* util::getParticles (util.cpp:51-57): which = 1 (current state) or 2 (sorted, rho/P). */
+int wc_download_particles(wc_handle* h, int32_t which, wc_particle* host_aos);
+
+/* Fluid::update(double time) (Fluid.cpp:342-354): sort(buf1->buf2); density(buf2);
+ * update(buf2->buf1, dt = frame_dt * time_scale).  Asynchronous on the handle's stream. */
+int wc_step(wc_handle* h, float frame_dt, const wc_step_params* sp);
+/* Stage-level entry points, like the reference's separate runXProg methods. */
+int wc_sort_only(wc_handle* h);                                      /* Sort::run, Sort.cpp:254 */
+int wc_density_only(wc_handle* h, const wc_step_params* sp);         /* Fluid.cpp:268 */
+int wc_update_only(wc_handle* h, float frame_dt, const wc_step_params* sp); /* Fluid.cpp:294 */
+
+/* util::getUints (util.cpp:65-71) for the sort outputs; any pointer may be NULL.
+ * cell_ids[n], counts[num_bins], offsets[num_bins], sorted_perm[n], neighbour_counts[n]. */
+int wc_download_cells(wc_handle* h, uint32_t* cell_ids, uint32_t* counts, uint32_t* offsets,
+                      uint32_t* sorted_perm, uint32_t* neighbour_counts);
+/* Total force F of update.comp:195 per particle of the last update (3 floats each);
+ * needs WC_FLAG_DEBUG_OUTPUTS. */
+int wc_download_forces(wc_handle* h, float* forces_xyz);
+
+/* Replace density/pressure (and everything else) of buffer 2 from host AoS: lets a test
+ * drive wc_update_only with arbitrary inputs, like binding an SSBO by hand. */
+int wc_upload_sorted(wc_handle* h, const wc_particle* host_aos, int32_t n);
+
+int wc_device_ptrs(wc_handle* h, wc_device_view* view);
+/* Pack buffer `which` (1 or 2) as 32-byte AoS into a DEVICE buffer (n * 32 bytes). */
+int wc_export_aos_device(wc_handle* h, int32_t which, void* device_dst);
+int wc_sync(wc_handle* h);
+
+/* Milliseconds per stage of the last wc_step (needs WC_FLAG_STAGE_TIMING; syncs). */
+int wc_stage_times(wc_handle* h, float ms[WC_NUM_STAGES]);
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int wc_launch_count(const wc_handle* h, uint64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

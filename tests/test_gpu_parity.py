@@ -1,0 +1,317 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle and the
+committed golden vectors.  Bars (BASELINE.json north_star / SURVEY.md 8d):
+
+* cell ids, counts, offsets, sorted permutation, neighbour counts: BIT-EXACT;
+* density, pressure, force, velocity, position after one step: fp32 tolerances below
+  (summation order differs from the oracle's, so not bit-exact);
+* multi-step runs: conserved / statistical quantities (trajectories are chaotic).
+
+Tolerances (calibrated by tests/test_oracle.py::test_f32_oracle_vs_f64_truth_error_budget,
+where the fp32 oracle itself sits within these of an fp64 evaluation):
+"""
+import os
+
+import numpy as np
+import pytest
+
+from watercube_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+RTOL_RHO = 1e-5            # density: relative
+RTOL_P = 3e-5              # pressure: relative to |P| + stiffness
+RTOL_F = 5e-5              # force: relative to the scene's max |F| (sums cancel)
+RTOL_V = 2e-5              # velocity: relative to the scene's max |v| (+ 1e-7 abs)
+ULPS_X = 2.0               # position: absolute, in ulps of the box size
+
+f32 = np.float32
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+FRAME_DT = 1.0 / 60.0
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from watercube_b200 import capi as m
+
+    m.lib()
+    return m
+
+
+def ulp(x):
+    return float(np.spacing(f32(x)))
+
+
+def oracle_params(oracle, sc, **overrides):
+    return oracle.default_params(num_particles=sc.n, size=sc.size, grid_res=sc.grid_res,
+                                 particle_radius=sc.particle_radius, **overrides)
+
+
+def gpu_fluid(capi, sc, flags, **step_kw):
+    return capi.Fluid(num_particles=sc.n, grid_res=sc.grid_res, size=sc.size,
+                      particle_radius=sc.particle_radius, flags=flags, **step_kw)
+
+
+def run_gpu_stages(capi, sc, simple, **step_kw):
+    flags = capi.FLAG_DEBUG_OUTPUTS | (capi.FLAG_SIMPLE_KERNELS if simple else 0)
+    with gpu_fluid(capi, sc, flags, **step_kw) as fl:
+        fl.upload(sc.particles)
+        fl.sort_only()
+        res = fl.cells()
+        res["sorted_in"] = fl.download(2)
+        fl.density_only()
+        res["neighbour_counts"] = fl.cells(neighbour_counts=True)["neighbour_counts"]
+        res["sorted"] = fl.download(2)
+        fl.update_only(FRAME_DT)
+        res["force"] = fl.forces()
+        res["out"] = fl.download(1)
+    return res
+
+
+def run_oracle_stages(oracle, sc, **overrides):
+    p = oracle_params(oracle, sc, **overrides)
+    d = oracle.derive(p)
+    s = oracle.sort(sc.particles, d.bin_size, p.grid_res)
+    P, nc = oracle.density(s["sorted"], s["counts"], s["offsets"], p, nthreads=oracle.max_threads())
+    dt = f32(FRAME_DT) * f32(p.time_scale)
+    out, F = oracle.update(P, s["counts"], s["offsets"], p, dt, nthreads=oracle.max_threads())
+    return dict(cell_ids=s["cell_ids"], counts=s["counts"], offsets=s["offsets"], perm=s["perm"],
+                sorted_in=oracle.as_f32(s["sorted"]), neighbour_counts=nc,
+                sorted=oracle.as_f32(P), force=F, out=oracle.as_f32(out), params=p)
+
+
+def assert_parity(got, ref, size, stiffness=100.0, stride=1):
+    for key in ("cell_ids", "counts", "offsets", "perm", "neighbour_counts"):
+        np.testing.assert_array_equal(got[key], ref[key], err_msg=key)       # bit-exact
+    if "sorted_in" in ref:
+        np.testing.assert_array_equal(got["sorted_in"], ref["sorted_in"])    # payload moved intact
+    g_rho, g_p = got["sorted"][::stride, 3], got["sorted"][::stride, 7]
+    r_rho, r_p = ref["density"], ref["pressure"]
+    np.testing.assert_allclose(g_rho, r_rho, rtol=RTOL_RHO, atol=0)
+    assert np.all(np.abs(g_p - r_p) <= RTOL_P * (np.abs(r_p) + stiffness))
+    gF, rF = got["force"][::stride], ref["force"]
+    assert np.max(np.abs(gF - rF)) <= RTOL_F * max(np.abs(rF).max(), 1e-30)
+    go, ro = got["out"][::stride], ref["out"]
+    vmax = max(np.abs(ro[:, 4:7]).max(), 1e-30)
+    assert np.max(np.abs(go[:, 4:7] - ro[:, 4:7])) <= RTOL_V * vmax + 1e-7
+    assert np.max(np.abs(go[:, 0:3] - ro[:, 0:3])) <= ULPS_X * ulp(size)
+    np.testing.assert_array_equal(go[:, 3], got["sorted"][::stride, 3])      # rho, P carried through
+    np.testing.assert_array_equal(go[:, 7], got["sorted"][::stride, 7])
+
+
+def ref_from_oracle(o):
+    r = dict(o)
+    r["density"], r["pressure"] = o["sorted"][:, 3], o["sorted"][:, 7]
+    return r
+
+
+# ------------------------------------------------------------------ golden fixtures
+@pytest.mark.parametrize("simple", [False, True], ids=["tiled", "simple"])
+@pytest.mark.parametrize("name", ["dam_break_4096", "uniform_3000", "default_80000"])
+def test_against_golden_vectors(capi, name, simple):
+    from tests.golden import make_golden
+
+    factory, overrides, stride = make_golden.CASES[name]
+    sc = factory()
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    got = run_gpu_stages(capi, sc, simple, **overrides)
+    assert_parity(got, g, sc.size, stride=stride)
+
+
+# ------------------------------------------------------------------ oracle, seeded inputs
+CASES = {
+    "ragged_777": lambda: scenes.dam_break(777, seed=4, size=0.2, grid_res=4),
+    "single": lambda: scenes.dam_break(1, seed=0, size=1.0, grid_res=21),
+    "dam_break_20000": lambda: scenes.dam_break(20000, seed=7),
+    "uniform_h_small": lambda: scenes.uniform_box(6000, size=0.5, h=0.03373, seed=8),
+    "uniform_h_large": lambda: scenes.uniform_box(6000, size=0.5, h=0.06349, seed=9),
+    "dam_break_scaled_200k": lambda: scenes.dam_break(200_000, seed=11),
+}
+
+
+@pytest.mark.parametrize("simple", [False, True], ids=["tiled", "simple"])
+@pytest.mark.parametrize("name", list(CASES))
+def test_against_oracle(capi, oracle, name, simple):
+    sc = CASES[name]()
+    ref = ref_from_oracle(run_oracle_stages(oracle, sc))
+    got = run_gpu_stages(capi, sc, simple)
+    assert_parity(got, ref, sc.size)
+
+
+@pytest.mark.parametrize("simple", [False, True], ids=["tiled", "simple"])
+def test_non_default_step_params_and_mouse(capi, oracle, simple):
+    sc = scenes.uniform_box(5000, size=0.45, h=0.04, seed=21)
+    kw = dict(gravity=[100.0, -500.0, 50.0], rest_pressure=40.0, stiffness=60.0,
+              rest_density=800.0, viscosity_coefficient=50.0,
+              mouse_origin=[0.2, 0.2, -1.0], mouse_dir=[0.0, 0.0, 1.0])
+    ref = ref_from_oracle(run_oracle_stages(oracle, sc, **kw))
+    got = run_gpu_stages(capi, sc, simple, **kw)
+    assert_parity(got, ref, sc.size, stiffness=60.0)
+
+
+def test_edge_positions_outside_box_nan_and_coincident(capi, oracle):
+    """Hash edge cases of count.comp:32 (Q11) + coincident particles (Q7)."""
+    sc = scenes.dam_break(3000, seed=5, size=0.3, grid_res=6)
+    P = sc.particles
+    P[0, :3] = [-0.2, 0.1, 0.1]
+    P[1, :3] = [0.5, 0.31, -3.0]
+    P[2, :3] = [0.3, 0.3, 0.3]
+    P[3, :3] = P[4, :3]          # coincident pair with different velocities
+    P[3, 4:7] = [1.0, 0.0, 0.0]
+    P[5, :3] = [1e30, -1e30, 0.0]
+    o = run_oracle_stages(oracle, sc)
+    with gpu_fluid(capi, sc, capi.FLAG_DEBUG_OUTPUTS) as fl:
+        fl.upload(P)
+        fl.sort_only()
+        got = fl.cells()
+    for key in ("cell_ids", "counts", "offsets", "perm"):
+        np.testing.assert_array_equal(got[key], o[key], err_msg=key)
+    # NaN position: hashes to cell 0 on both sides; only the integer outputs are defined
+    P[6, :3] = [np.nan, 0.1, np.nan]
+    o = run_oracle_stages(oracle, sc)
+    with gpu_fluid(capi, sc, 0) as fl:
+        fl.upload(P)
+        fl.sort_only()
+        got = fl.cells()
+    for key in ("cell_ids", "counts", "offsets", "perm"):
+        np.testing.assert_array_equal(got[key], o[key], err_msg=key)
+
+
+def test_all_particles_in_one_cell(capi, oracle):
+    """Worst case for the in-cell rank fix-up and for cell-list imbalance."""
+    n = 3000
+    rng = np.random.default_rng(0)
+    P = np.zeros((n, 8), f32)
+    P[:, :3] = 0.5 + rng.uniform(0, 0.04, (n, 3)).astype(f32)
+    sc = scenes.Scene("one_cell", P, 1.0, 21, 0.01)
+    ref = ref_from_oracle(run_oracle_stages(oracle, sc))
+    assert (ref["counts"] > 0).sum() <= 8
+    for simple in (False, True):
+        got = run_gpu_stages(capi, sc, simple)
+        assert_parity(got, ref, sc.size)
+
+
+def test_empty_and_reupload(capi, oracle):
+    sc = scenes.dam_break(5000, seed=2, size=0.4, grid_res=8)
+    with capi.Fluid(num_particles=0, capacity=5000, grid_res=sc.grid_res, size=sc.size,
+                    flags=capi.FLAG_DEBUG_OUTPUTS) as fl:
+        fl.step(FRAME_DT)                                 # n = 0 is a no-op, not an error
+        cells = fl.cells()
+        assert cells["counts"].sum() == 0 and cells["offsets"].max() == 0
+        fl.upload(sc.particles)                           # grow within capacity
+        assert fl.num_particles == 5000
+        fl.step(FRAME_DT)
+        out = fl.download(1)
+        with pytest.raises(capi.WcError):
+            fl.upload(np.zeros((5001, 8), f32))           # beyond capacity: loud error
+    st = oracle.Stepper(sc.particles, oracle_params(oracle, sc), nthreads=4)
+    st.step(FRAME_DT)
+    ro = oracle.as_f32(st.buf1)
+    assert np.max(np.abs(out[:, 0:3] - ro[:, 0:3])) <= ULPS_X * ulp(sc.size)
+
+
+# ------------------------------------------------------------------ whole step
+def test_step_equals_stage_composition_and_is_deterministic(capi):
+    sc = scenes.dam_break(50000, seed=3)
+    outs = []
+    for mode in ("step", "stages", "step"):
+        with gpu_fluid(capi, sc, 0) as fl:
+            fl.upload(sc.particles)
+            for _ in range(3):
+                if mode == "step":
+                    fl.step(FRAME_DT)
+                else:
+                    fl.sort_only()
+                    fl.density_only()
+                    fl.update_only(FRAME_DT)
+            outs.append((fl.download(1), fl.download(2)))
+    for a, b in zip(outs[0], outs[1]):
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(outs[0], outs[2]):                    # run-to-run bit-identical
+        np.testing.assert_array_equal(a, b)
+
+
+def test_simple_and_tiled_kernels_agree_bitwise_on_integers(capi):
+    sc = scenes.dam_break(120000, seed=13)
+    res = [run_gpu_stages(capi, sc, simple) for simple in (False, True)]
+    for key in ("cell_ids", "counts", "offsets", "perm", "neighbour_counts"):
+        np.testing.assert_array_equal(res[0][key], res[1][key])
+    np.testing.assert_allclose(res[0]["sorted"][:, 3], res[1]["sorted"][:, 3], rtol=RTOL_RHO)
+
+
+def conserved(A, m):
+    x, v, rho = A[:, 0:3].astype(np.float64), A[:, 4:7].astype(np.float64), A[:, 3]
+    return dict(mass=m * len(A), momentum=m * v.sum(0), kinetic=0.5 * m * (v * v).sum(),
+                com=x.mean(0), vmax=np.abs(v).max(), clamp_frac=(np.abs(v) >= 50.0).mean(),
+                rho=rho.astype(np.float64))
+
+
+def test_default_scene_multi_step_statistics(capi, oracle):
+    """BASELINE config 1 (shortened to 40 steps for CI time; bench.py --config default runs
+    the 1000-step version): compare conserved / statistical quantities, not trajectories."""
+    sc = scenes.dam_break(80000, seed=0)
+    steps = 40
+    p = oracle_params(oracle, sc)
+    st = oracle.Stepper(sc.particles, p, nthreads=oracle.max_threads())
+    with gpu_fluid(capi, sc, 0) as fl:
+        fl.upload(sc.particles)
+        for _ in range(steps):
+            fl.step(FRAME_DT)
+            st.step(FRAME_DT)
+        G1, G2 = fl.download(1), fl.download(2)
+    O1 = oracle.as_f32(st.buf1)
+    assert np.isfinite(G1).all()                                             # particle.vert:36-46
+    assert G1[:, :3].min() >= f32(0.001) and G1[:, :3].max() <= f32(1.0) - f32(0.001)
+    assert (G2[:, 3] > 0).all() and np.abs(G1[:, 4:7]).max() <= 50.0
+    m = float(oracle.derive(p).particle_mass)
+    cg, co = conserved(G1, m), conserved(O1, m)
+    assert cg["mass"] == co["mass"]
+    ke_scale = co["kinetic"]
+    assert abs(cg["kinetic"] - co["kinetic"]) <= 2e-2 * ke_scale
+    mom_scale = m * np.abs(O1[:, 4:7]).sum()
+    assert np.all(np.abs(cg["momentum"] - co["momentum"]) <= 2e-2 * mom_scale)
+    assert np.all(np.abs(cg["com"] - co["com"]) <= 1e-3)
+    assert abs(cg["vmax"] - co["vmax"]) <= 0.2 * co["vmax"] + 1e-3
+    assert abs(cg["clamp_frac"] - co["clamp_frac"]) <= 1e-3
+    # density-error distribution: two-sample Kolmogorov-Smirnov distance of rho / rho0
+    a, b = np.sort(cg["rho"]), np.sort(co["rho"])
+    grid = np.concatenate([a, b])
+    ks = np.max(np.abs(np.searchsorted(a, grid, side="right") / len(a)
+                       - np.searchsorted(b, grid, side="right") / len(b)))
+    assert ks < 0.02
+
+
+# ------------------------------------------------------------------ BASELINE sizes: properties
+@pytest.mark.parametrize("n", [1_000_000, 16_000_000])
+def test_full_size_properties(capi, n):
+    """At BASELINE.json's sizes the oracle is too slow; check size-independent properties:
+    histogram total, exclusive scan, permutation, sortedness, stability, idempotence of the
+    sort, finite in-box outputs and run-to-run determinism."""
+    sc = scenes.dam_break(n, seed=0)
+    with gpu_fluid(capi, sc, capi.FLAG_DEBUG_OUTPUTS) as fl:
+        fl.upload(sc.particles)
+        fl.step(FRAME_DT)
+        cells = fl.cells(neighbour_counts=True)
+        out1, srt = fl.download(1), fl.download(2)
+        counts, offsets, perm, ids = (cells[k] for k in ("counts", "offsets", "perm", "cell_ids"))
+        assert counts.sum() == n
+        np.testing.assert_array_equal(offsets, np.concatenate([[0], np.cumsum(counts)[:-1]]))
+        seen = np.zeros(n, bool)
+        seen[perm] = True
+        assert seen.all()                                                    # a permutation
+        sid = ids[perm].astype(np.int64)
+        assert np.all(np.diff(sid) >= 0)                                     # sorted by cell
+        assert np.all(np.diff(perm.astype(np.int64))[np.diff(sid) == 0] > 0)  # stable (Q1)
+        np.testing.assert_array_equal(srt[:, [0, 1, 2, 4, 5, 6]],
+                                      sc.particles[perm][:, [0, 1, 2, 4, 5, 6]])
+        nc = cells["neighbour_counts"]
+        assert 35 < nc.mean() < 60 and nc.max() < 200
+        assert np.isfinite(out1).all()
+        assert out1[:, :3].min() >= f32(0.001) and out1[:, :3].max() <= f32(sc.size) - f32(0.001)
+        # idempotence: the sorted buffer re-sorted is the identity permutation
+        fl.upload(srt)
+        fl.sort_only()
+        np.testing.assert_array_equal(fl.cells()["perm"], np.arange(n, dtype=np.uint32))
+    with gpu_fluid(capi, sc, 0) as fl:                                       # determinism
+        fl.upload(sc.particles)
+        fl.step(FRAME_DT)
+        np.testing.assert_array_equal(fl.download(1), out1)

@@ -1,0 +1,277 @@
+"""ctypes binding of include/wc_sph.h plus a thin Python mirror of core::Fluid.
+
+This is glue for tests and bench.py; the product is the native library.  There is no CPU
+fallback: a missing library or device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+LIB_PATH = os.path.join(_CSRC, "libwc_sph.so")
+
+WC_OK, WC_ERR_INVALID, WC_ERR_NO_DEVICE, WC_ERR_CUDA, WC_ERR_CAPACITY = 0, 1, 2, 3, 4
+FLAG_DEBUG_OUTPUTS, FLAG_STAGE_TIMING, FLAG_SIMPLE_KERNELS = 1, 2, 4
+STAGES = ("hash_count", "scan", "reorder", "density", "update")
+NUM_STAGES = len(STAGES)
+
+PARTICLE_DTYPE = np.dtype(
+    [("position", np.float32, 3), ("density", np.float32), ("velocity", np.float32, 3),
+     ("pressure", np.float32)]
+)
+
+# Every symbol include/wc_sph.h declares (checked by tests/test_capi_cpu.py).
+EXPORTS = (
+    "wc_abi_version", "wc_last_error", "wc_default_params", "wc_default_step_params", "wc_derive",
+    "wc_create", "wc_destroy", "wc_get_derived", "wc_upload_particles", "wc_download_particles",
+    "wc_step", "wc_sort_only", "wc_density_only", "wc_update_only", "wc_download_cells",
+    "wc_download_forces", "wc_upload_sorted", "wc_device_ptrs", "wc_export_aos_device", "wc_sync",
+    "wc_stage_times", "wc_launch_count",
+)
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("num_particles", C.c_int32), ("capacity", C.c_int32), ("grid_res", C.c_int32),
+        ("size", C.c_float), ("particle_radius", C.c_float), ("time_scale", C.c_float),
+        ("device", C.c_int32), ("flags", C.c_uint32), ("stream", C.c_void_p),
+    ]
+
+
+class StepParams(C.Structure):
+    _fields_ = [
+        ("viscosity_coefficient", C.c_float), ("stiffness", C.c_float),
+        ("rest_density", C.c_float), ("rest_pressure", C.c_float),
+        ("gravity", C.c_float * 3), ("mouse_origin", C.c_float * 3), ("mouse_dir", C.c_float * 3),
+    ]
+
+
+class Derived(C.Structure):
+    _fields_ = [
+        ("num_bins", C.c_int32), ("bin_size", C.c_float), ("kernel_radius", C.c_float),
+        ("particle_mass", C.c_float), ("poly6_const", C.c_float), ("spiky_const", C.c_float),
+        ("visc_const", C.c_float), ("dist2_threshold", C.c_float),
+    ]
+
+
+class DeviceView(C.Structure):
+    _fields_ = [
+        ("pos_rho", C.c_void_p * 2), ("vel_pres", C.c_void_p * 2), ("cell_ids", C.c_void_p),
+        ("counts", C.c_void_p), ("offsets", C.c_void_p), ("sorted", C.c_void_p),
+        ("neighbour_counts", C.c_void_p), ("forces", C.c_void_p), ("stream", C.c_void_p),
+        ("num_particles", C.c_int32), ("capacity", C.c_int32),
+    ]
+
+
+class WcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"wc_sph error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libwc_sph.so (raises loudly when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m watercube_b200.build` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
+        L.wc_abi_version.restype = C.c_int
+        L.wc_last_error.restype = C.c_char_p
+        sig = {
+            "wc_default_params": [C.POINTER(Params)],
+            "wc_default_step_params": [C.POINTER(StepParams)],
+            "wc_derive": [C.POINTER(Params), C.POINTER(Derived)],
+            "wc_create": [C.POINTER(Params), C.POINTER(vp)],
+            "wc_destroy": [vp],
+            "wc_get_derived": [vp, C.POINTER(Derived)],
+            "wc_upload_particles": [vp, vp, i32],
+            "wc_download_particles": [vp, i32, vp],
+            "wc_step": [vp, f32, C.POINTER(StepParams)],
+            "wc_sort_only": [vp],
+            "wc_density_only": [vp, C.POINTER(StepParams)],
+            "wc_update_only": [vp, f32, C.POINTER(StepParams)],
+            "wc_download_cells": [vp, vp, vp, vp, vp, vp],
+            "wc_download_forces": [vp, vp],
+            "wc_upload_sorted": [vp, vp, i32],
+            "wc_device_ptrs": [vp, C.POINTER(DeviceView)],
+            "wc_export_aos_device": [vp, i32, vp],
+            "wc_sync": [vp],
+            "wc_stage_times": [vp, C.POINTER(C.c_float * NUM_STAGES)],
+            "wc_launch_count": [vp, C.POINTER(C.c_uint64)],
+        }
+        for name, argtypes in sig.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != WC_OK:
+        raise WcError(rc, lib().wc_last_error().decode(errors="replace"))
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    check(lib().wc_default_params(C.byref(p)))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def default_step_params(**kw) -> StepParams:
+    sp = StepParams()
+    check(lib().wc_default_step_params(C.byref(sp)))
+    for k, v in kw.items():
+        if k in ("gravity", "mouse_origin", "mouse_dir"):
+            getattr(sp, k)[:] = [float(x) for x in v]
+        else:
+            setattr(sp, k, v)
+    return sp
+
+
+def derive(p: Params) -> Derived:
+    d = Derived()
+    check(lib().wc_derive(C.byref(p), C.byref(d)))
+    return d
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _as_aos(a) -> np.ndarray:
+    a = np.ascontiguousarray(a)
+    if a.dtype == PARTICLE_DTYPE:
+        return a.view(np.float32).reshape(-1, 8)
+    return np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 8)
+
+
+class Fluid:
+    """Python mirror of core::Fluid's setup/update/particle-buffer surface
+    (src/core/Fluid.h:32-59) on top of the C-ABI."""
+
+    def __init__(self, num_particles=80000, grid_res=21, size=1.0, particle_radius=0.01,
+                 time_scale=0.012, device=0, flags=0, stream=None, capacity=0, **step_kw):
+        self.params = default_params(num_particles=num_particles, grid_res=grid_res, size=size,
+                                     particle_radius=particle_radius, time_scale=time_scale,
+                                     device=device, flags=flags, capacity=capacity,
+                                     stream=stream)
+        self.step_params = default_step_params(**step_kw)
+        self._h = C.c_void_p()
+        check(lib().wc_create(C.byref(self.params), C.byref(self._h)))
+        self.derived = Derived()
+        check(lib().wc_get_derived(self._h, C.byref(self.derived)))
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().wc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- particle-buffer surface
+    @property
+    def num_particles(self) -> int:
+        return int(self.view().num_particles)
+
+    def upload(self, particles):
+        """util::setParticles into buffer 1.  Accepts ndarray or a raw host pointer + n."""
+        if isinstance(particles, tuple):
+            ptr, n = particles
+            check(lib().wc_upload_particles(self._h, C.c_void_p(ptr), int(n)))
+            return
+        a = _as_aos(particles)
+        check(lib().wc_upload_particles(self._h, _ptr(a), a.shape[0]))
+
+    def upload_sorted(self, particles):
+        a = _as_aos(particles)
+        check(lib().wc_upload_sorted(self._h, _ptr(a), a.shape[0]))
+
+    def download(self, which=1, out=None) -> np.ndarray:
+        """util::getParticles: which=1 current state, which=2 sorted with density/pressure."""
+        if isinstance(out, tuple):
+            check(lib().wc_download_particles(self._h, int(which), C.c_void_p(out[0])))
+            return None
+        n = self.num_particles
+        if out is None:
+            out = np.empty((n, 8), np.float32)
+        check(lib().wc_download_particles(self._h, int(which), _ptr(out)))
+        return out
+
+    # -- stepping
+    def step(self, frame_dt=1.0 / 60.0):
+        """Fluid::update(double time)"""
+        check(lib().wc_step(self._h, float(frame_dt), C.byref(self.step_params)))
+
+    update = step
+
+    def sort_only(self):
+        check(lib().wc_sort_only(self._h))
+
+    def density_only(self):
+        check(lib().wc_density_only(self._h, C.byref(self.step_params)))
+
+    def update_only(self, frame_dt=1.0 / 60.0):
+        check(lib().wc_update_only(self._h, float(frame_dt), C.byref(self.step_params)))
+
+    def sync(self):
+        check(lib().wc_sync(self._h))
+
+    # -- inspection
+    def cells(self, neighbour_counts=False):
+        n, nb = self.num_particles, int(self.derived.num_bins)
+        out = dict(cell_ids=np.empty(n, np.uint32), counts=np.empty(nb, np.uint32),
+                   offsets=np.empty(nb, np.uint32), perm=np.empty(n, np.uint32))
+        nc = np.empty(n, np.uint32) if neighbour_counts else None
+        check(lib().wc_download_cells(self._h, _ptr(out["cell_ids"]), _ptr(out["counts"]),
+                                      _ptr(out["offsets"]), _ptr(out["perm"]), _ptr(nc)))
+        if neighbour_counts:
+            out["neighbour_counts"] = nc
+        return out
+
+    def forces(self) -> np.ndarray:
+        F = np.empty((self.num_particles, 3), np.float32)
+        check(lib().wc_download_forces(self._h, _ptr(F)))
+        return F
+
+    def view(self) -> DeviceView:
+        v = DeviceView()
+        check(lib().wc_device_ptrs(self._h, C.byref(v)))
+        return v
+
+    def stage_times(self):
+        ms = (C.c_float * NUM_STAGES)()
+        check(lib().wc_stage_times(self._h, C.byref(ms)))
+        return dict(zip(STAGES, [float(x) for x in ms]))
+
+    def launch_count(self) -> int:
+        v = C.c_uint64()
+        check(lib().wc_launch_count(self._h, C.byref(v)))
+        return int(v.value)

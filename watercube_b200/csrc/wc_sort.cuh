@@ -1,0 +1,204 @@
+// wc_sort.cuh -- cell-hash binning and the STABLE counting sort.
+//
+// Replaces the reference's three sort dispatches (src/core/Sort.cpp:254-267):
+//   count.comp:25-36      -> k_hash_count   (warp-aggregated atomics, also records the
+//                                            arrival rank so no second atomic pass runs)
+//   linearScan.comp:15-28 -> k_scan         (single-pass decoupled look-back scan instead of
+//                                            the 1-thread serial loop, Sort.cpp:181-184)
+//   reorder.comp:32-45    -> k_scatter_ids + k_reorder (sort.comp:32-45's ID scatter followed
+//                                            by an in-cell rank fix-up that makes the order
+//                                            the canonical ascending-input-index one, Q1)
+#pragma once
+
+#include "wc_common.cuh"
+
+namespace wc {
+
+// ---------------------------------------------------------------------------------------
+// AoS (32-byte struct Particle, src/core/util.h:29-35) <-> SoA float4 pairs.
+__global__ void k_aos_to_soa(const float4* __restrict__ aos, int n, float4* __restrict__ pos_rho,
+                             float4* __restrict__ vel_pres) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pos_rho[i] = aos[2 * (size_t)i];
+    vel_pres[i] = aos[2 * (size_t)i + 1];
+}
+
+__global__ void k_soa_to_aos(const float4* __restrict__ pos_rho,
+                             const float4* __restrict__ vel_pres, int n,
+                             float4* __restrict__ aos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    aos[2 * (size_t)i] = pos_rho[i];
+    aos[2 * (size_t)i + 1] = vel_pres[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// count.comp:25-36.  One thread per particle; lanes of a warp that hit the same cell are
+// merged with __match_any_sync so one atomicAdd serves the whole group (the input of
+// step k+1 is the cell-sorted output of step k, so groups are long).  rank = arrival
+// order within the cell; it is NOT the stable rank (k_reorder fixes that up).
+__global__ void __launch_bounds__(256)
+k_hash_count(const float4* __restrict__ pos_rho, int n, float bin, int G,
+             uint32_t* __restrict__ cell_ids, uint32_t* __restrict__ ranks,
+             uint32_t* __restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n;
+    uint32_t c = 0xFFFFFFFFu;
+    if (active) {
+        const float4 p = pos_rho[i];
+        c = cell_index(p.x, p.y, p.z, bin, G);
+    }
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned group = __match_any_sync(0xffffffffu, c);
+    if (active) {
+        const int leader = __ffs(group) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(&counts[c], (uint32_t)__popc(group));
+        base = __shfl_sync(group, base, leader);
+        cell_ids[i] = c;
+        ranks[i] = base + (uint32_t)__popc(group & ((1u << lane) - 1u));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// linearScan.comp:15-28 as a single-pass chained scan with decoupled look-back.
+// status[tile] packs {flag:2 | value:32} in one 64-bit word so flag and value are
+// published atomically.  status[] and *tile_counter must be zero at launch (they live in
+// the same per-step cleared arena as counts[]).
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr unsigned long long kFlagAgg = 1ull << 32;
+constexpr unsigned long long kFlagIncl = 2ull << 32;
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+    *reinterpret_cast<volatile unsigned long long*>(p) = v;
+}
+
+// Writes out[i] = sum(in[0..i)) for i < n and out[n] = sum(in[0..n)).
+__global__ void __launch_bounds__(kScanThreads)
+k_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n,
+       unsigned long long* __restrict__ status, unsigned int* __restrict__ tile_counter) {
+    __shared__ unsigned int s_tile;
+    __shared__ uint32_t s_warp[kScanThreads / kWarp];
+    __shared__ uint32_t s_prefix;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const int tile = (int)s_tile;
+    const int base = tile * kScanTile + tid * kScanItems;
+
+    uint32_t v[kScanItems];
+    if (base + kScanItems <= n) {  // in[] is 256-byte aligned and base is a multiple of 4
+        const uint4 q = *reinterpret_cast<const uint4*>(in + base);
+        v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) v[k] = (base + k < n) ? in[base + k] : 0u;
+    }
+    const uint32_t tsum = v[0] + v[1] + v[2] + v[3];
+
+    // block-wide exclusive scan of the per-thread sums
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane];
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        s_warp[lane] = winc - w;  // exclusive prefix of warp totals
+        const uint32_t aggregate = __shfl_sync(0xffffffffu, winc, 31);
+
+        // decoupled look-back (warp 0)
+        uint32_t prefix = 0;
+        if (tile > 0) {
+            if (lane == 0) st_status(&status[tile], kFlagAgg | aggregate);
+            int look = tile - 1;
+            while (true) {
+                const int idx = look - lane;
+                unsigned long long s = kFlagIncl;  // virtual tile -1: inclusive prefix 0
+                if (idx >= 0) {
+                    do {
+                        s = ld_status(&status[idx]);
+                    } while ((s >> 32) == 0ull);
+                }
+                const unsigned incl_mask = __ballot_sync(0xffffffffu, (s >> 32) == 2ull);
+                uint32_t val = (uint32_t)s;
+                if (incl_mask) {
+                    const int first = __ffs(incl_mask) - 1;
+                    if (lane > first) val = 0;
+                    prefix += warp_sum(val);
+                    break;
+                }
+                prefix += warp_sum(val);
+                look -= 32;
+            }
+        }
+        if (lane == 0) {
+            st_status(&status[tile], kFlagIncl | (unsigned long long)(prefix + aggregate));
+            s_prefix = prefix;
+        }
+    }
+    __syncthreads();
+
+    uint32_t run = s_prefix + s_warp[warp] + (incl - tsum);
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+        if (base + k == n - 1) out[n] = run;
+    }
+    if (n == 0 && tile == 0 && tid == 0) out[0] = 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// sort.comp:41-44: sorted[offsets[cell] + localOffset] = particleID, with the arrival rank
+// recorded by k_hash_count standing in for the second atomicAdd pass.
+__global__ void __launch_bounds__(256)
+k_scatter_ids(const uint32_t* __restrict__ cell_ids, const uint32_t* __restrict__ ranks,
+              const uint32_t* __restrict__ offsets, int n, uint32_t* __restrict__ ids) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ids[offsets[cell_ids[i]] + ranks[i]] = (uint32_t)i;
+}
+
+// reorder.comp:32-45 made stable.  One thread per slot j of the arrival-ordered ID list:
+// it owns particle id = ids[j], finds its cell's slice [beg, end) and counts the IDs in the
+// slice that are smaller: that is the stable rank (what the serial oracle loop produces).
+// Threads of one cell walk the same slice in lockstep, so the loads are warp broadcasts.
+// The payload moves as two float4 (SoA), and the permutation is kept (sort.comp's output).
+__global__ void __launch_bounds__(256)
+k_reorder(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ offsets, int n, float bin,
+          int G, const float4* __restrict__ pos_in, const float4* __restrict__ vel_in,
+          float4* __restrict__ pos_out, float4* __restrict__ vel_out,
+          uint32_t* __restrict__ perm) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t id = ids[j];
+    const float4 p = pos_in[id];
+    const float4 v = vel_in[id];
+    const uint32_t c = cell_index(p.x, p.y, p.z, bin, G);
+    const uint32_t beg = offsets[c], end = offsets[c + 1];
+    uint32_t rank = 0;
+    for (uint32_t k = beg; k < end; k++) rank += (ids[k] < id) ? 1u : 0u;
+    const uint32_t dst = beg + rank;
+    pos_out[dst] = p;
+    vel_out[dst] = v;
+    perm[dst] = id;
+}
+
+}  // namespace wc
