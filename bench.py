@@ -102,7 +102,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.gpu)],
+                 "-lms", "50", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -229,7 +229,9 @@ def run_b200(args):
     n_total = args.particles or 1_000_000
     sc = make_scene(args, n_total)
     n = sc.n
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream, so torch.cuda.Event sees the library's launches
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     flags = capi.FLAG_STAGE_TIMING | (capi.FLAG_SIMPLE_KERNELS if args.simple_kernels else 0)
     fl = capi.Fluid(num_particles=n, grid_res=sc.grid_res, size=sc.size,
                     particle_radius=sc.particle_radius, device=local, flags=flags,

@@ -18,10 +18,12 @@ from watercube_b200 import scenes
 
 pytestmark = pytest.mark.gpu
 
-RTOL_RHO = 1e-5            # density: relative
+RTOL_RHO = 1e-5            # density: relative to |rho| + |wall term| (the z-branch quirk Q2/Q3
+                           # can make the wall term a huge negative number that cancels)
 RTOL_P = 3e-5              # pressure: relative to |P| + stiffness
 RTOL_F = 5e-5              # force: relative to the scene's max |F| (sums cancel)
-RTOL_V = 2e-5              # velocity: relative to the scene's max |v| (+ 1e-7 abs)
+RTOL_V = 2e-5              # velocity: relative to the scene's max(|v|, |F| / rho * dt) (+ 1e-7):
+                           # the +-50 clamp (update.comp:199) hides the scale of a * dt
 ULPS_X = 2.0               # position: absolute, in ulps of the box size
 
 f32 = np.float32
@@ -79,19 +81,32 @@ def run_oracle_stages(oracle, sc, **overrides):
                 sorted=oracle.as_f32(P), force=F, out=oracle.as_f32(out), params=p)
 
 
-def assert_parity(got, ref, size, stiffness=100.0, stride=1):
+def wall_term_magnitude(sorted_particles, size, h):
+    """|wallDensity| per particle (density.comp:57-79), for the cancellation-aware tolerance."""
+    from tests import refmath
+
+    c = dict(h=f32(h), m=f32(2.0 * h), size=f32(size),
+             poly6C=f32(315.0 / (64.0 * np.pi * float(f32(h)) ** 9)))
+    with np.errstate(all="ignore"):
+        return np.abs(refmath.wall_density(c, sorted_particles[:, :3]))
+
+
+def assert_parity(got, ref, size, stiffness=100.0, stride=1, h=0.04):
     for key in ("cell_ids", "counts", "offsets", "perm", "neighbour_counts"):
         np.testing.assert_array_equal(got[key], ref[key], err_msg=key)       # bit-exact
     if "sorted_in" in ref:
         np.testing.assert_array_equal(got["sorted_in"], ref["sorted_in"])    # payload moved intact
     g_rho, g_p = got["sorted"][::stride, 3], got["sorted"][::stride, 7]
     r_rho, r_p = ref["density"], ref["pressure"]
-    np.testing.assert_allclose(g_rho, r_rho, rtol=RTOL_RHO, atol=0)
+    wall = wall_term_magnitude(got["sorted_in"] if "sorted_in" in got else got["sorted"], size,
+                               h)[::stride]
+    assert np.all(np.abs(g_rho - r_rho) <= RTOL_RHO * (np.abs(r_rho) + wall))
     assert np.all(np.abs(g_p - r_p) <= RTOL_P * (np.abs(r_p) + stiffness))
     gF, rF = got["force"][::stride], ref["force"]
     assert np.max(np.abs(gF - rF)) <= RTOL_F * max(np.abs(rF).max(), 1e-30)
     go, ro = got["out"][::stride], ref["out"]
-    vmax = max(np.abs(ro[:, 4:7]).max(), 1e-30)
+    dt = float(f32(FRAME_DT) * f32(0.012))
+    vmax = max(np.abs(ro[:, 4:7]).max(), float((np.abs(rF).max(1) / np.abs(r_rho)).max()) * dt)
     assert np.max(np.abs(go[:, 4:7] - ro[:, 4:7])) <= RTOL_V * vmax + 1e-7
     assert np.max(np.abs(go[:, 0:3] - ro[:, 0:3])) <= ULPS_X * ulp(size)
     np.testing.assert_array_equal(go[:, 3], got["sorted"][::stride, 3])      # rho, P carried through
@@ -114,7 +129,7 @@ def test_against_golden_vectors(capi, name, simple):
     sc = factory()
     g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
     got = run_gpu_stages(capi, sc, simple, **overrides)
-    assert_parity(got, g, sc.size, stride=stride)
+    assert_parity(got, g, sc.size, stride=stride, h=4.0 * sc.particle_radius)
 
 
 # ------------------------------------------------------------------ oracle, seeded inputs
@@ -134,7 +149,7 @@ def test_against_oracle(capi, oracle, name, simple):
     sc = CASES[name]()
     ref = ref_from_oracle(run_oracle_stages(oracle, sc))
     got = run_gpu_stages(capi, sc, simple)
-    assert_parity(got, ref, sc.size)
+    assert_parity(got, ref, sc.size, h=4.0 * sc.particle_radius)
 
 
 @pytest.mark.parametrize("simple", [False, True], ids=["tiled", "simple"])
@@ -145,7 +160,7 @@ def test_non_default_step_params_and_mouse(capi, oracle, simple):
               mouse_origin=[0.2, 0.2, -1.0], mouse_dir=[0.0, 0.0, 1.0])
     ref = ref_from_oracle(run_oracle_stages(oracle, sc, **kw))
     got = run_gpu_stages(capi, sc, simple, **kw)
-    assert_parity(got, ref, sc.size, stiffness=60.0)
+    assert_parity(got, ref, sc.size, stiffness=60.0, h=4.0 * sc.particle_radius)
 
 
 def test_edge_positions_outside_box_nan_and_coincident(capi, oracle):
