@@ -74,6 +74,9 @@ typedef struct wc_params {
     float time_scale;       /* Fluid.cpp:24, default 0.012: dt = frame_dt * time_scale */
     int32_t device;         /* CUDA device ordinal */
     uint32_t flags;         /* WC_FLAG_* */
+    int32_t neighbour_list_words; /* per 32-particle group: capacity of the density->update
+                               neighbour list in 32-candidate words; 0 = default (32),
+                               < 0 = no list (update repeats the search) */
     void* stream;           /* optional caller-owned cudaStream_t; NULL = library-owned */
 } wc_params;
 

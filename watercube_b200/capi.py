@@ -37,7 +37,8 @@ class Params(C.Structure):
     _fields_ = [
         ("num_particles", C.c_int32), ("capacity", C.c_int32), ("grid_res", C.c_int32),
         ("size", C.c_float), ("particle_radius", C.c_float), ("time_scale", C.c_float),
-        ("device", C.c_int32), ("flags", C.c_uint32), ("stream", C.c_void_p),
+        ("device", C.c_int32), ("flags", C.c_uint32), ("neighbour_list_words", C.c_int32),
+        ("stream", C.c_void_p),
     ]
 
 
@@ -167,11 +168,12 @@ class Fluid:
     (src/core/Fluid.h:32-59) on top of the C-ABI."""
 
     def __init__(self, num_particles=80000, grid_res=21, size=1.0, particle_radius=0.01,
-                 time_scale=0.012, device=0, flags=0, stream=None, capacity=0, **step_kw):
+                 time_scale=0.012, device=0, flags=0, stream=None, capacity=0,
+                 neighbour_list_words=0, **step_kw):
         self.params = default_params(num_particles=num_particles, grid_res=grid_res, size=size,
                                      particle_radius=particle_radius, time_scale=time_scale,
                                      device=device, flags=flags, capacity=capacity,
-                                     stream=stream)
+                                     neighbour_list_words=neighbour_list_words, stream=stream)
         self.step_params = default_step_params(**step_kw)
         self._h = C.c_void_p()
         check(lib().wc_create(C.byref(self.params), C.byref(self._h)))

@@ -97,6 +97,12 @@ struct wc_handle {
     uint32_t* offsets = nullptr;          // num_bins + 1
     uint32_t* neighbour_counts = nullptr;
     float4* forces = nullptr;
+    // density -> update neighbour list (wc_sph_tile.cuh NbrList)
+    uint32_t* nbr_idx = nullptr;
+    uint32_t* nbr_mask = nullptr;
+    uint32_t* nbr_words = nullptr;
+    int nbr_cap_words = 0;
+    bool nbr_valid = false;
 
     // Arena cleared once per sort: counts | scan status | scan tile counter.
     void* arena = nullptr;
@@ -175,6 +181,7 @@ int run_sort(wc_handle* h, bool timed) {
     }
     if (timed && (rc = record(h, 3))) return rc;
     h->sorted_valid = true;
+    h->nbr_valid = false;
     return WC_OK;
 }
 
@@ -182,10 +189,12 @@ int run_density(wc_handle* h, const wc_step_params& sp) {
     if (h->n == 0) return WC_OK;
     const SphConsts c = make_consts(h, sp, 0.0f);
     const bool dbg = h->p.flags & WC_FLAG_DEBUG_OUTPUTS;
+    const NbrList list{h->nbr_idx, h->nbr_mask, h->nbr_words, h->nbr_cap_words};
     int rc = (h->p.flags & WC_FLAG_SIMPLE_KERNELS)
                  ? -1
                  : launch_density_tile(h->pos[1], h->vel[1], h->offsets, c,
-                                       dbg ? h->neighbour_counts : nullptr, h->stream);
+                                       dbg ? h->neighbour_counts : nullptr, list, h->stream);
+    h->nbr_valid = (rc == 0) && h->nbr_idx != nullptr;
     if (rc == -1) {  // geometry the tile kernel does not cover: simple path
         if (dbg)
             k_density_v1<true><<<div_up(h->n, 128), 128, 0, h->stream>>>(
@@ -202,10 +211,14 @@ int run_update(wc_handle* h, const wc_step_params& sp, float frame_dt) {
     if (h->n == 0) return WC_OK;
     const SphConsts c = make_consts(h, sp, frame_dt);
     const bool dbg = h->p.flags & WC_FLAG_DEBUG_OUTPUTS;
+    // The list is only trusted when the density pass that built it saw these positions.
+    const NbrList list = h->nbr_valid
+                             ? NbrList{h->nbr_idx, h->nbr_mask, h->nbr_words, h->nbr_cap_words}
+                             : NbrList{nullptr, nullptr, nullptr, 0};
     int rc = (h->p.flags & WC_FLAG_SIMPLE_KERNELS)
                  ? -1
                  : launch_update_tile(h->pos[1], h->vel[1], h->offsets, c, h->pos[0], h->vel[0],
-                                      dbg ? h->forces : nullptr, h->stream);
+                                      dbg ? h->forces : nullptr, list, h->stream);
     if (rc == -1) {
         if (dbg)
             k_update_v1<true><<<div_up(h->n, 128), 128, 0, h->stream>>>(
@@ -242,6 +255,7 @@ int wc_default_params(wc_params* p) {
     p->time_scale = 0.012f;     // Fluid.cpp:24
     p->device = 0;
     p->flags = 0;
+    p->neighbour_list_words = 0;
     p->stream = nullptr;
     return WC_OK;
 }
@@ -356,6 +370,13 @@ int wc_create(const wc_params* p, wc_handle** out) {
     WC_ALLOC(h->perm, capz * sizeof(uint32_t));
     WC_ALLOC(h->offsets, (nb + 1) * sizeof(uint32_t));
     WC_ALLOC(h->arena, h->arena_bytes);
+    if (p->neighbour_list_words >= 0 && !(p->flags & WC_FLAG_SIMPLE_KERNELS)) {
+        h->nbr_cap_words = p->neighbour_list_words > 0 ? p->neighbour_list_words : 32;
+        const size_t warps = (size_t)tile_warps(cap);
+        WC_ALLOC(h->nbr_idx, warps * h->nbr_cap_words * 32 * sizeof(uint32_t));
+        WC_ALLOC(h->nbr_mask, warps * h->nbr_cap_words * 32 * sizeof(uint32_t));
+        WC_ALLOC(h->nbr_words, warps * sizeof(uint32_t));
+    }
     if (p->flags & WC_FLAG_DEBUG_OUTPUTS) {
         WC_ALLOC(h->neighbour_counts, capz * sizeof(uint32_t));
         WC_ALLOC(h->forces, capz * sizeof(float4));
@@ -406,6 +427,9 @@ int wc_destroy(wc_handle* h) {
     cudaFree(h->arena);
     cudaFree(h->neighbour_counts);
     cudaFree(h->forces);
+    cudaFree(h->nbr_idx);
+    cudaFree(h->nbr_mask);
+    cudaFree(h->nbr_words);
     for (int i = 0; i <= WC_NUM_STAGES; i++)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -442,6 +466,7 @@ int wc_upload_particles(wc_handle* h, const wc_particle* host_aos, int32_t n) {
 
 int wc_upload_sorted(wc_handle* h, const wc_particle* host_aos, int32_t n) {
     if (h && n != h->n) return fail(WC_ERR_INVALID, "n = %d differs from num_particles %d", n, h->n);
+    if (h) h->nbr_valid = false;  // positions may have changed under the neighbour list
     return upload_into(h, 1, host_aos, n);
 }
 

@@ -39,13 +39,34 @@ __device__ __forceinline__ float warp_max_f(float v) {
     return v;
 }
 
+constexpr uint32_t kNoIndex = 0xFFFFFFFFu;     // padding slot in a staged / listed word
+constexpr uint32_t kListOverflow = 0xFFFFFFFFu;  // nbr_words value: list did not fit
+
+// self_seq[t] = position (word * 32 + bit) at which target lane t's own particle appears in
+// the warp's candidate sequence, recorded when it is staged (density.comp:110: the particle
+// itself is not a neighbour, so its bit is cleared from the masks).
 struct DensityStage {
     float4 a[kStageCap];
+    uint32_t j[kStageCap];
+    uint32_t self_seq[32];
 };
 struct UpdateStage {
     float4 a[kStageCap];
     float4 b[kStageCap];
     uint32_t j[kStageCap];
+    uint32_t self_seq[32];
+};
+
+// Neighbour list handed from the density pass to the update pass.  For every 32-target
+// warp the density kernel records, word by word, which 32 staged candidates it looked at
+// (nbr_idx) and which of them each lane accepted (nbr_mask, one bit per candidate).  The
+// update kernel replays the words: no second cull, no second distance test.  Layout:
+// [(warp * cap_words + word) * 32 + lane], i.e. one coalesced 128-byte line per word.
+struct NbrList {
+    uint32_t* idx;
+    uint32_t* mask;
+    uint32_t* words;  // per warp: number of words, or kListOverflow
+    int cap_words;
 };
 
 // Per-lane accumulators and the batch processors -----------------------------------------
@@ -53,28 +74,93 @@ template <bool kDebug>
 struct DensityAcc {
     float sum = 0.0f;
     uint32_t nn = 0;
+    uint32_t words_used = 0;
+    bool overflow = false;
+    uint32_t* idx_out = nullptr;   // already offset to this warp's first word + lane
+    uint32_t* mask_out = nullptr;
+    int cap_words = 0;
     // Runs this lane's target over stage[0, count); count is a multiple of 32.
     __device__ __forceinline__ void process(const DensityStage& st, int count, const SphConsts& c,
                                             float4 p, float4, float Teff, uint32_t) {
+        const int lane = threadIdx.x & 31;
+        const uint32_t self_seq = st.self_seq[lane];
         for (int k0 = 0; k0 < count; k0 += 32) {
+            unsigned mk = 0u;
 #pragma unroll
             for (int k = 0; k < 32; k++) {
                 const float4 q = st.a[k0 + k];
                 const float d2 = dist2(p.x - q.x, p.y - q.y, p.z - q.z);
                 if (d2 < Teff) {  // density.comp:117; the self pair (d2 = 0) is the m*poly6(0) term
                     sum += poly6_t3(c.h2, d2);
-                    if (kDebug) nn++;
+                    mk |= 1u << k;
                 }
             }
+            if (words_used == (self_seq >> 5)) mk &= ~(1u << (self_seq & 31u));  // density.comp:110
+            if (kDebug) nn += (uint32_t)__popc(mk);
+            if (idx_out) {
+                if (words_used < (uint32_t)cap_words) {
+                    idx_out[(size_t)words_used * 32] = st.j[k0 + lane];
+                    mask_out[(size_t)words_used * 32] = mk;
+                } else {
+                    overflow = true;
+                }
+            }
+            words_used++;
         }
     }
 };
 
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Stage layout of the update pass: a = (x, y, z, 1/rho), b = (vx, vy, vz, P).
 struct UpdateAcc {
+    // Fp is accumulated without its factor -0.5 * m * spikyC, Fv without m * viscC.
     float Fpx = 0, Fpy = 0, Fpz = 0, Fvx = 0, Fvy = 0, Fvz = 0;
+    uint32_t words_used = 0;  // words of the candidate sequence processed so far (full path)
+
+    // One accepted pair of update.comp:174-187.
+    __device__ __forceinline__ void pair(const SphConsts& c, float4 p, float4 v, float4 qa,
+                                         float4 qb) {
+        const float rx = p.x - qa.x, ry = p.y - qa.y, rz = p.z - qa.z;
+        const float d2 = dist2(rx, ry, rz);
+        const float inv_d = rsqrt_approx(fmaxf(d2, 1e-32f));  // Q7: dist == 0 -> r/d adds 0
+        const float hd = c.h - d2 * inv_d;
+        const float S = (v.w + qb.w) * qa.w;                   // 2 * (Pi+Pj)/(2 rho_j)
+        const float w = S > 0.0f ? (S * (hd * hd)) * inv_d : 0.0f;  // Q9
+        Fpx = fmaf(w, rx, Fpx), Fpy = fmaf(w, ry, Fpy), Fpz = fmaf(w, rz, Fpz);
+        const float wv = hd * qa.w;                            // update.comp:186-187
+        Fvx = fmaf(wv, qb.x - v.x, Fvx), Fvy = fmaf(wv, qb.y - v.y, Fvy),
+        Fvz = fmaf(wv, qb.z - v.z, Fvz);
+    }
+
+    // phase 2: every lane walks its own accepted candidates.  The four mask words of a batch
+    // sit in a per-lane shift register (m0 is the word being drained, base its first slot),
+    // so a lane moves on to its next word while others are still busy with theirs.
+    __device__ __forceinline__ void pairs(const UpdateStage& st, unsigned m0, unsigned m1,
+                                          unsigned m2, unsigned m3, const SphConsts& c, float4 p,
+                                          float4 v) {
+        int base = 0;
+        while (__any_sync(0xffffffffu, (m0 | m1 | m2 | m3) != 0u)) {
+            if (m0 == 0u) {
+                m0 = m1, m1 = m2, m2 = m3, m3 = 0u;
+                base += 32;
+            }
+            if (m0 != 0u) {
+                const int slot = base + __ffs((int)m0) - 1;
+                m0 &= m0 - 1u;
+                pair(c, p, v, st.a[slot], st.b[slot]);
+            }
+        }
+    }
+
+    // Full path (no list): phase 1 = distance test only -> one bit per staged candidate.
     __device__ __forceinline__ void process(const UpdateStage& st, int count, const SphConsts& c,
-                                            float4 p, float4 v, float Teff, uint32_t self) {
-        // phase 1: distance test only -> one bit per staged candidate
+                                            float4 p, float4 v, float Teff, uint32_t) {
+        const uint32_t self_seq = st.self_seq[threadIdx.x & 31];
         unsigned mk[kChunk / 32];
 #pragma unroll
         for (int w = 0; w < kChunk / 32; w++) {
@@ -86,33 +172,14 @@ struct UpdateAcc {
                     const float d2 = dist2(p.x - q.x, p.y - q.y, p.z - q.z);
                     mk[w] |= (d2 < Teff) ? (1u << k) : 0u;
                 }
+                if (words_used == (self_seq >> 5)) mk[w] &= ~(1u << (self_seq & 31u));
+                words_used++;
             }
         }
-        // phase 2: every lane walks its own accepted candidates (update.comp:174-187)
-        unsigned long long m0 = (unsigned long long)mk[0] | ((unsigned long long)mk[1] << 32);
-        unsigned long long m1 = (unsigned long long)mk[2] | ((unsigned long long)mk[3] << 32);
-        while (__any_sync(0xffffffffu, (m0 | m1) != 0ull)) {
-            if ((m0 | m1) != 0ull) {
-                int slot;
-                if (m0) {
-                    slot = __ffsll((long long)m0) - 1;
-                    m0 &= m0 - 1ull;
-                } else {
-                    slot = 64 + __ffsll((long long)m1) - 1;
-                    m1 &= m1 - 1ull;
-                }
-                if (st.j[slot] != self) {  // update.comp:164 (particleID == otherParticleID)
-                    const float4 qa = st.a[slot];
-                    const float4 qb = st.b[slot];
-                    const float rx = p.x - qa.x, ry = p.y - qa.y, rz = p.z - qa.z;
-                    pair_force(c, rx, ry, rz, dist2(rx, ry, rz), v.w, v, qa.w, qb, Fpx, Fpy, Fpz,
-                               Fvx, Fvy, Fvz);
-                }
-            }
-        }
+        pairs(st, mk[0], mk[1], mk[2], mk[3], c, p, v);
     }
 };
-static_assert(kChunk == 128, "UpdateAcc::process packs the masks into two 64-bit words");
+static_assert(kChunk == 128, "UpdateAcc::pairs drains four 32-bit mask words per batch");
 
 // The shared gather driver ----------------------------------------------------------------
 // kUpdate selects what is staged (positions only, or positions + velocities + index).
@@ -132,6 +199,9 @@ __device__ __forceinline__ void gather_rows(const float4* pos_rho, const float4*
         row = cz * G + cy;
     }
     const float Tcull = c.T * 1.0001f;  // conservative: rounding in the box distance
+    const uint32_t wfirst = self - (uint32_t)lane;  // index of the warp's first target
+    st.self_seq[lane] = kNoIndex;
+    __syncwarp();
 
     unsigned rem = __ballot_sync(full, valid);
     while (rem) {
@@ -185,11 +255,13 @@ __device__ __forceinline__ void gather_rows(const float4* pos_rho, const float4*
                 const unsigned km = __ballot_sync(full, keep);
                 if (keep) {
                     const int slot = cnt + __popc(km & lt);
-                    st.a[slot] = q;
                     if constexpr (kUpdate) {
+                        q.w = __frcp_rn(q.w);  // the pair force only needs 1/rho_j
                         st.b[slot] = vel_pres[j];
-                        st.j[slot] = j;
                     }
+                    st.a[slot] = q;
+                    st.j[slot] = j;
+                    if (j - wfirst < 32u) st.self_seq[j - wfirst] = acc.words_used * 32u + (uint32_t)slot;
                 }
                 cnt += __popc(km);
                 j0 += 32;
@@ -198,7 +270,10 @@ __device__ __forceinline__ void gather_rows(const float4* pos_rho, const float4*
                 int count = kChunk;
                 if (cnt < kChunk) {  // final partial batch: pad to a multiple of 32
                     count = (cnt + 31) & ~31;
-                    if (cnt + lane < count) st.a[cnt + lane] = make_float4(kFar, kFar, kFar, 0.0f);
+                    if (cnt + lane < count) {
+                        st.a[cnt + lane] = make_float4(kFar, kFar, kFar, 0.0f);
+                        st.j[cnt + lane] = kNoIndex;
+                    }
                 }
                 __syncwarp();
                 acc.process(st, count, c, p, v, Teff, self);
@@ -211,18 +286,14 @@ __device__ __forceinline__ void gather_rows(const float4* pos_rho, const float4*
                     const bool mv = lane < left;
                     if (mv) {
                         ta = st.a[kChunk + lane];
-                        if constexpr (kUpdate) {
-                            tb = st.b[kChunk + lane];
-                            tj = st.j[kChunk + lane];
-                        }
+                        tj = st.j[kChunk + lane];
+                        if constexpr (kUpdate) tb = st.b[kChunk + lane];
                     }
                     __syncwarp();
                     if (mv) {
                         st.a[lane] = ta;
-                        if constexpr (kUpdate) {
-                            st.b[lane] = tb;
-                            st.j[lane] = tj;
-                        }
+                        st.j[lane] = tj;
+                        if constexpr (kUpdate) st.b[lane] = tb;
                     }
                     __syncwarp();
                 }
@@ -237,33 +308,45 @@ template <bool kDebug>
 __global__ void __launch_bounds__(kTileWarps * 32)
 k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
                const uint32_t* __restrict__ offsets, SphConsts c,
-               uint32_t* __restrict__ neighbour_counts) {
+               uint32_t* __restrict__ neighbour_counts, NbrList list) {
     __shared__ DensityStage s_stage[kTileWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = (blockIdx.x * kTileWarps + warp) * 32 + lane;
+    const int wg = blockIdx.x * kTileWarps + warp;
+    const int i = wg * 32 + lane;
     const bool valid = i < c.n;
     float4 p = make_float4(0, 0, 0, 0);
     if (valid) p = pos_rho[i];
     DensityAcc<kDebug> acc;
+    if (list.idx) {
+        acc.idx_out = list.idx + (size_t)wg * list.cap_words * 32 + lane;
+        acc.mask_out = list.mask + (size_t)wg * list.cap_words * 32 + lane;
+        acc.cap_words = list.cap_words;
+    }
     gather_rows<false>(pos_rho, vel_pres, offsets, c, s_stage[warp], acc, valid, (uint32_t)i, p,
                        make_float4(0, 0, 0, 0));
+    if (list.idx && lane == 0 && wg * 32 < c.n)
+        list.words[wg] = acc.overflow ? kListOverflow : acc.words_used;
     if (!valid) return;
     float rho, pres;
     finish_density(c, acc.sum, p.x, p.y, p.z, &rho, &pres);
     // In place like density.comp:135; the gather only reads x,y,z, which do not change.
     reinterpret_cast<float*>(pos_rho)[4 * (size_t)i + 3] = rho;
     reinterpret_cast<float*>(vel_pres)[4 * (size_t)i + 3] = pres;
-    if (kDebug) neighbour_counts[i] = acc.nn - 1u;  // minus the self pair
+    if (kDebug) neighbour_counts[i] = acc.nn;  // the self pair's bit is already cleared
 }
 
+// update.comp:134-232.  With a valid neighbour list the warp replays the density pass's
+// words (gather by index into the stage, then pairs()); without one (list.idx == nullptr,
+// or this warp overflowed its list) it runs the full cull + distance test itself.
 template <bool kDebug>
 __global__ void __launch_bounds__(kTileWarps * 32)
 k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel_pres,
               const uint32_t* __restrict__ offsets, SphConsts c, float4* __restrict__ pos_out,
-              float4* __restrict__ vel_out, float4* __restrict__ forces) {
+              float4* __restrict__ vel_out, float4* __restrict__ forces, NbrList list) {
     __shared__ UpdateStage s_stage[kTileWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = (blockIdx.x * kTileWarps + warp) * 32 + lane;
+    const int wg = blockIdx.x * kTileWarps + warp;
+    const int i = wg * 32 + lane;
     const bool valid = i < c.n;
     float4 p = make_float4(0, 0, 0, 0), v = make_float4(0, 0, 0, 0);
     if (valid) {
@@ -271,9 +354,43 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
         v = vel_pres[i];
     }
     UpdateAcc acc;
-    gather_rows<true>(pos_rho, vel_pres, offsets, c, s_stage[warp], acc, valid, (uint32_t)i, p, v);
+    UpdateStage& st = s_stage[warp];
+    uint32_t nw = kListOverflow;
+    if (list.idx && wg * 32 < c.n) nw = list.words[wg];
+    if (nw == kListOverflow) {
+        if (wg * 32 < c.n)
+            gather_rows<true>(pos_rho, vel_pres, offsets, c, st, acc, valid, (uint32_t)i, p, v);
+    } else {
+        const uint32_t* widx = list.idx + (size_t)wg * list.cap_words * 32 + lane;
+        const uint32_t* wmask = list.mask + (size_t)wg * list.cap_words * 32 + lane;
+        for (uint32_t w0 = 0; w0 < nw; w0 += kChunk / 32) {
+            unsigned mk[kChunk / 32];
+            uint32_t jj[kChunk / 32];
+#pragma unroll
+            for (int u = 0; u < kChunk / 32; u++) {
+                mk[u] = 0u;
+                jj[u] = kNoIndex;
+                if (w0 + u < nw) {
+                    jj[u] = widx[(size_t)(w0 + u) * 32];
+                    mk[u] = wmask[(size_t)(w0 + u) * 32];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kChunk / 32; u++) {
+                if (jj[u] != kNoIndex) {
+                    float4 qa = pos_rho[jj[u]];
+                    qa.w = __frcp_rn(qa.w);
+                    st.a[u * 32 + lane] = qa;
+                    st.b[u * 32 + lane] = vel_pres[jj[u]];
+                }
+            }
+            __syncwarp();
+            acc.pairs(st, mk[0], mk[1], mk[2], mk[3], c, p, v);
+            __syncwarp();
+        }
+    }
     if (!valid) return;
-    const float kp = -(c.m * c.spikyC), kv = c.m * c.viscC;
+    const float kp = -0.5f * (c.m * c.spikyC), kv = c.m * c.viscC;
     float4 po, vo, fo;
     integrate(c, p, v, acc.Fpx * kp, acc.Fpy * kp, acc.Fpz * kp, acc.Fvx * kv, acc.Fvy * kv,
               acc.Fvz * kv, &po, &vo, kDebug ? &fo : nullptr);
@@ -283,29 +400,31 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
 }
 
 inline int tile_blocks(int n) { return (n + kTileWarps * 32 - 1) / (kTileWarps * 32); }
+inline int tile_warps(int n) { return tile_blocks(n) * kTileWarps; }
 
 // Returns 0 when launched, -1 when the geometry is not covered (never, currently).
 inline int launch_density_tile(float4* pos_rho, float4* vel_pres, const uint32_t* offsets,
-                               const SphConsts& c, uint32_t* neighbour_counts,
+                               const SphConsts& c, uint32_t* neighbour_counts, NbrList list,
                                cudaStream_t stream) {
     if (neighbour_counts)
         k_density_tile<true><<<tile_blocks(c.n), kTileWarps * 32, 0, stream>>>(
-            pos_rho, vel_pres, offsets, c, neighbour_counts);
+            pos_rho, vel_pres, offsets, c, neighbour_counts, list);
     else
         k_density_tile<false><<<tile_blocks(c.n), kTileWarps * 32, 0, stream>>>(
-            pos_rho, vel_pres, offsets, c, nullptr);
+            pos_rho, vel_pres, offsets, c, nullptr, list);
     return 0;
 }
 
 inline int launch_update_tile(const float4* pos_rho, const float4* vel_pres,
                               const uint32_t* offsets, const SphConsts& c, float4* pos_out,
-                              float4* vel_out, float4* forces, cudaStream_t stream) {
+                              float4* vel_out, float4* forces, NbrList list,
+                              cudaStream_t stream) {
     if (forces)
         k_update_tile<true><<<tile_blocks(c.n), kTileWarps * 32, 0, stream>>>(
-            pos_rho, vel_pres, offsets, c, pos_out, vel_out, forces);
+            pos_rho, vel_pres, offsets, c, pos_out, vel_out, forces, list);
     else
         k_update_tile<false><<<tile_blocks(c.n), kTileWarps * 32, 0, stream>>>(
-            pos_rho, vel_pres, offsets, c, pos_out, vel_out, nullptr);
+            pos_rho, vel_pres, offsets, c, pos_out, vel_out, nullptr, list);
     return 0;
 }
 
