@@ -77,6 +77,12 @@ typedef struct wc_params {
     int32_t neighbour_list_words; /* per 32-particle group: capacity of the density->update
                                neighbour list in 32-candidate words; 0 = default (32),
                                < 0 = no list (update repeats the search) */
+    /* z-slab mode (multi-GPU, one handle per rank): this handle owns the global z-layers
+     * [slab_z_begin, slab_z_end) of the grid.  Enabled when slab_ghost_capacity > 0;
+     * `capacity` then bounds the OWNED particles.  See the wc_slab_* calls below. */
+    int32_t slab_z_begin, slab_z_end;
+    int32_t slab_ghost_capacity;   /* max particles of ONE neighbouring halo layer */
+    int32_t slab_migrant_capacity; /* max particles crossing ONE slab face per step */
     void* stream;           /* optional caller-owned cudaStream_t; NULL = library-owned */
 } wc_params;
 
@@ -167,6 +173,46 @@ int wc_device_ptrs(wc_handle* h, wc_device_view* view);
 /* Pack buffer `which` (1 or 2) as 32-byte AoS into a DEVICE buffer (n * 32 bytes). */
 int wc_export_aos_device(wc_handle* h, int32_t which, void* device_dst);
 int wc_sync(wc_handle* h);
+
+/* ---- z-slab decomposition (new; the reference is single-GPU) --------------
+ * One step on a slab handle is the call sequence below; the caller moves the listed device
+ * buffers between neighbouring ranks (NCCL / any transport) between the calls.  Direction
+ * index 0 = the rank below (lower z), 1 = the rank above.  A missing neighbour's receive
+ * buffers must be zero-filled (wc_slab_clear_recv).
+ *   wc_slab_sort_count   unpack mig_in, hash + count + scan of the owned layers
+ *     exchange lc_send[d] -> neighbour's lc_recv[1-d]              (lc_bytes each)
+ *   wc_slab_sync_info    host sync; returns the particle counts of this step
+ *   wc_slab_reorder      ghost-layer offsets + stable reorder of the owned particles
+ *     exchange halo positions: first / last owned layer of buffer 2 -> neighbour's ghost slots
+ *   wc_slab_density
+ *     exchange halo positions (now carrying density) and velocities/pressures
+ *   wc_slab_update       force + integrate, then extraction of particles that left the slab
+ *     exchange mig_out[d] -> neighbour's mig_in[1-d]               (mig_bytes each)
+ * Concatenating the ranks' buffers in z order gives bit-identical results to one
+ * whole-grid handle (tests/test_slab_gpu.py). */
+typedef struct wc_slab_view {
+    void* mig_out[2];
+    void* mig_in[2];
+    void* lc_send[2];
+    void* lc_recv[2];
+    void* pos_rho_sorted;  /* float4 buffer 2; owned particles start at index owned_first */
+    void* vel_pres_sorted;
+    uint64_t mig_bytes;    /* size of one migrant message: 32-byte header + capacity * 32 */
+    uint64_t lc_bytes;     /* size of one layer-count message: 4 * (1 + grid_res^2) */
+    int32_t owned_first;   /* = slab_ghost_capacity */
+    int32_t reserved;
+} wc_slab_view;
+
+/* info[8] = { n_owned, n_first_layer, n_last_layer, n_ghost_below, n_ghost_above,
+ *             errors (capacity overflows / lost migrants, sticky), migrants_in_below,
+ *             migrants_in_above } */
+int wc_slab_get_view(wc_handle* h, wc_slab_view* view);
+int wc_slab_clear_recv(wc_handle* h, int32_t direction);
+int wc_slab_sort_count(wc_handle* h);
+int wc_slab_sync_info(wc_handle* h, int32_t info[8]);
+int wc_slab_reorder(wc_handle* h);
+int wc_slab_density(wc_handle* h, const wc_step_params* sp);
+int wc_slab_update(wc_handle* h, float frame_dt, const wc_step_params* sp);
 
 /* Milliseconds per stage of the last wc_step (needs WC_FLAG_STAGE_TIMING; syncs). */
 int wc_stage_times(wc_handle* h, float ms[WC_NUM_STAGES]);

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(capi):
 
 
 def test_struct_layouts_match_header(capi):
-    assert C.sizeof(capi.Params) == 48          # 9 x 4 bytes, padding, pointer
+    assert C.sizeof(capi.Params) == 64          # 13 x 4 bytes, padding, pointer
     assert C.sizeof(capi.StepParams) == 52
     assert C.sizeof(capi.Derived) == 32
     assert capi.PARTICLE_DTYPE.itemsize == 32   # src/core/util.h:29-35

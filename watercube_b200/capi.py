@@ -29,7 +29,9 @@ EXPORTS = (
     "wc_create", "wc_destroy", "wc_get_derived", "wc_upload_particles", "wc_download_particles",
     "wc_step", "wc_sort_only", "wc_density_only", "wc_update_only", "wc_download_cells",
     "wc_download_forces", "wc_upload_sorted", "wc_device_ptrs", "wc_export_aos_device", "wc_sync",
-    "wc_stage_times", "wc_launch_count",
+    "wc_stage_times", "wc_launch_count", "wc_slab_get_view", "wc_slab_clear_recv",
+    "wc_slab_sort_count", "wc_slab_sync_info", "wc_slab_reorder", "wc_slab_density",
+    "wc_slab_update",
 )
 
 
@@ -38,6 +40,8 @@ class Params(C.Structure):
         ("num_particles", C.c_int32), ("capacity", C.c_int32), ("grid_res", C.c_int32),
         ("size", C.c_float), ("particle_radius", C.c_float), ("time_scale", C.c_float),
         ("device", C.c_int32), ("flags", C.c_uint32), ("neighbour_list_words", C.c_int32),
+        ("slab_z_begin", C.c_int32), ("slab_z_end", C.c_int32),
+        ("slab_ghost_capacity", C.c_int32), ("slab_migrant_capacity", C.c_int32),
         ("stream", C.c_void_p),
     ]
 
@@ -65,6 +69,19 @@ class DeviceView(C.Structure):
         ("neighbour_counts", C.c_void_p), ("forces", C.c_void_p), ("stream", C.c_void_p),
         ("num_particles", C.c_int32), ("capacity", C.c_int32),
     ]
+
+
+class SlabView(C.Structure):
+    _fields_ = [
+        ("mig_out", C.c_void_p * 2), ("mig_in", C.c_void_p * 2), ("lc_send", C.c_void_p * 2),
+        ("lc_recv", C.c_void_p * 2), ("pos_rho_sorted", C.c_void_p),
+        ("vel_pres_sorted", C.c_void_p), ("mig_bytes", C.c_uint64), ("lc_bytes", C.c_uint64),
+        ("owned_first", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+SLAB_INFO = ("n_owned", "n_first", "n_last", "n_ghost_below", "n_ghost_above", "errors",
+             "migrants_in_below", "migrants_in_above")
 
 
 class WcError(RuntimeError):
@@ -109,6 +126,13 @@ def lib():
             "wc_sync": [vp],
             "wc_stage_times": [vp, C.POINTER(C.c_float * NUM_STAGES)],
             "wc_launch_count": [vp, C.POINTER(C.c_uint64)],
+            "wc_slab_get_view": [vp, C.POINTER(SlabView)],
+            "wc_slab_clear_recv": [vp, i32],
+            "wc_slab_sort_count": [vp],
+            "wc_slab_sync_info": [vp, C.POINTER(C.c_int32 * 8)],
+            "wc_slab_reorder": [vp],
+            "wc_slab_density": [vp, C.POINTER(StepParams)],
+            "wc_slab_update": [vp, f32, C.POINTER(StepParams)],
         }
         for name, argtypes in sig.items():
             fn = getattr(L, name)
@@ -169,11 +193,14 @@ class Fluid:
 
     def __init__(self, num_particles=80000, grid_res=21, size=1.0, particle_radius=0.01,
                  time_scale=0.012, device=0, flags=0, stream=None, capacity=0,
-                 neighbour_list_words=0, **step_kw):
+                 neighbour_list_words=0, slab=None, **step_kw):
         self.params = default_params(num_particles=num_particles, grid_res=grid_res, size=size,
                                      particle_radius=particle_radius, time_scale=time_scale,
                                      device=device, flags=flags, capacity=capacity,
                                      neighbour_list_words=neighbour_list_words, stream=stream)
+        if slab is not None:  # (z_begin, z_end, ghost_capacity, migrant_capacity)
+            (self.params.slab_z_begin, self.params.slab_z_end, self.params.slab_ghost_capacity,
+             self.params.slab_migrant_capacity) = [int(x) for x in slab]
         self.step_params = default_step_params(**step_kw)
         self._h = C.c_void_p()
         check(lib().wc_create(C.byref(self.params), C.byref(self._h)))
@@ -245,6 +272,32 @@ class Fluid:
 
     def sync(self):
         check(lib().wc_sync(self._h))
+
+    # -- z-slab mode (see include/wc_sph.h, wc_slab_*)
+    def slab_view(self) -> SlabView:
+        v = SlabView()
+        check(lib().wc_slab_get_view(self._h, C.byref(v)))
+        return v
+
+    def slab_clear_recv(self, direction):
+        check(lib().wc_slab_clear_recv(self._h, int(direction)))
+
+    def slab_sort_count(self):
+        check(lib().wc_slab_sort_count(self._h))
+
+    def slab_sync_info(self) -> dict:
+        info = (C.c_int32 * 8)()
+        check(lib().wc_slab_sync_info(self._h, C.byref(info)))
+        return dict(zip(SLAB_INFO, [int(x) for x in info]))
+
+    def slab_reorder(self):
+        check(lib().wc_slab_reorder(self._h))
+
+    def slab_density(self):
+        check(lib().wc_slab_density(self._h, C.byref(self.step_params)))
+
+    def slab_update(self, frame_dt=1.0 / 60.0):
+        check(lib().wc_slab_update(self._h, float(frame_dt), C.byref(self.step_params)))
 
     # -- inspection
     def cells(self, neighbour_counts=False):

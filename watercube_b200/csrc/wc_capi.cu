@@ -13,6 +13,7 @@
 #include <new>
 
 #include "wc_common.cuh"
+#include "wc_slab.cuh"
 #include "wc_sort.cuh"
 #include "wc_sph_tile.cuh"
 #include "wc_sph_v1.cuh"
@@ -114,6 +115,30 @@ struct wc_handle {
     cudaEvent_t ev[WC_NUM_STAGES + 1] = {};
     bool have_times = false;
     bool sorted_valid = false;
+
+    // ---- z-slab mode (wc_slab.cuh); all zero / false for a whole-grid handle
+    bool slab = false;
+    int z_begin = 0, z_end = 0;  // owned global z-layers [z_begin, z_end)
+    int Lz = 0;                  // layers of the local table: owned + 2 ghost layers (or G)
+    int zbase = 0;               // global layer of local layer 0
+    int M = 0;                   // migrant slots on either side of buffer 1's owned region
+    int Cg = 0;                  // ghost slots on either side of buffer 2's owned region
+    int n_first = 0, n_last = 0, n_glow = 0, n_ghigh = 0;  // of the current step (host copies)
+    int n_in_old = 0;            // owned count of the input (before this step's migration)
+    bool info_valid = false;
+    float4* mig_out[2] = {nullptr, nullptr};   // [0] to rank-1, [1] to rank+1 (header + AoS)
+    float4* mig_in[2] = {nullptr, nullptr};    // [0] from rank-1, [1] from rank+1
+    uint32_t* lc_send[2] = {nullptr, nullptr}; // layer-count messages [n, G*G counts]
+    uint32_t* lc_recv[2] = {nullptr, nullptr};
+    uint32_t* flags = nullptr;                 // migrant flags / slots scratch (2 x cap each)
+    uint32_t* slots = nullptr;
+    uint32_t* errors = nullptr;                // sticky device-side error counter
+    uint32_t* m_in = nullptr;                  // [2] received migrant counts (in arena)
+    uint32_t* info_dev = nullptr;              // [8] (in arena)
+    uint32_t* info_host = nullptr;             // pinned
+    unsigned long long* scan_status_x[4] = {}; // extra scan states: ghost-low, ghost-high, mig 0/1
+    unsigned int* scan_counter_x[4] = {};
+    size_t mig_bytes = 0, lc_bytes = 0;
 };
 
 namespace {
@@ -123,7 +148,10 @@ using namespace wc;
 SphConsts make_consts(const wc_handle* h, const wc_step_params& sp, float frame_dt) {
     SphConsts c;
     c.n = h->n;
+    c.first = h->Cg;
     c.G = h->p.grid_res;
+    c.Gz = h->Lz;
+    c.zbase = h->zbase;
     c.bin = h->d.bin_size;
     c.size = h->p.size;
     c.h = h->d.kernel_radius;
@@ -152,37 +180,81 @@ int record(wc_handle* h, int idx) {
     return WC_OK;
 }
 
-// Sort::run (Sort.cpp:254-267).
-int run_sort(wc_handle* h, bool timed) {
-    const int n = h->n, G = h->p.grid_res;
+// Sort::run part 1 (Sort.cpp:255-259): clear, count, scan.  In slab mode the input is the
+// virtual array [migrants from below | owned | migrants from above] and only the owned
+// layers are scanned (the ghost layers' offsets come from the neighbours' counts).
+int sort_count_phase(wc_handle* h, bool timed) {
+    const int G = h->p.grid_res;
     const float bin = h->d.bin_size;
     int rc;
     if (timed && (rc = record(h, 0))) return rc;
     // clearCountBuffer (Sort.cpp:255) -- one memset also resets the scan bookkeeping.
     WC_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
-    if (n > 0) {
-        k_hash_count<<<div_up(n, 256), 256, 0, h->stream>>>(h->pos[0], n, bin, G, h->cell_ids,
-                                                             h->ranks, h->counts);
+    if (!h->slab) {
+        if (h->n > 0) {
+            k_hash_count<<<div_up(h->n, 256), 256, 0, h->stream>>>(h->pos[0], h->n, bin, G,
+                                                                    h->cell_ids, h->ranks,
+                                                                    h->counts);
+            WC_CHECK_LAUNCH(h);
+        }
+        if (timed && (rc = record(h, 1))) return rc;
+        k_scan<<<div_up(h->num_bins, kScanTile), kScanThreads, 0, h->stream>>>(
+            h->counts, h->offsets, h->num_bins, h->scan_status, h->scan_counter, 0u);
         WC_CHECK_LAUNCH(h);
+        if (timed && (rc = record(h, 2))) return rc;
+        return WC_OK;
     }
+    const int G2 = G * G, M = h->M, n_old = h->n_in_old, total = M + n_old + M;
+    // received migrants -> the slots before / after the owned region of buffer 1
+    k_unpack_migrants<<<div_up(M, 256), 256, 0, h->stream>>>(h->mig_in[0], M, h->pos[0], h->vel[0],
+                                                           h->m_in + 0);
+    WC_CHECK_LAUNCH(h);
+    k_unpack_migrants<<<div_up(M, 256), 256, 0, h->stream>>>(
+        h->mig_in[1], M, h->pos[0] + M + n_old, h->vel[0] + M + n_old, h->m_in + 1);
+    WC_CHECK_LAUNCH(h);
+    k_hash_count_slab<<<div_up(total, 256), 256, 0, h->stream>>>(
+        h->pos[0], total, M, n_old, h->m_in, bin, G, h->z_begin, h->z_end, h->cell_ids, h->ranks,
+        h->counts, h->errors);
+    WC_CHECK_LAUNCH(h);
     if (timed && (rc = record(h, 1))) return rc;
-    k_scan<<<div_up(h->num_bins, kScanTile), kScanThreads, 0, h->stream>>>(
-        h->counts, h->offsets, h->num_bins, h->scan_status, h->scan_counter);
+    const int owned_bins = (h->Lz - 2) * G2;
+    k_scan<<<div_up(owned_bins, kScanTile), kScanThreads, 0, h->stream>>>(
+        h->counts + G2, h->offsets + G2, owned_bins, h->scan_status, h->scan_counter,
+        (uint32_t)h->Cg);
+    WC_CHECK_LAUNCH(h);
+    k_slab_info<<<div_up(G2, 256), 256, 0, h->stream>>>(h->counts, h->offsets, G2, h->Lz,
+                                                       (uint32_t)h->Cg, h->info_dev,
+                                                       h->lc_send[0], h->lc_send[1]);
     WC_CHECK_LAUNCH(h);
     if (timed && (rc = record(h, 2))) return rc;
-    if (n > 0) {
-        k_scatter_ids<<<div_up(n, 256), 256, 0, h->stream>>>(h->cell_ids, h->ranks, h->offsets, n,
-                                                              h->ids);
+    h->info_valid = false;
+    return WC_OK;
+}
+
+// Sort::run part 2 (Sort.cpp:263-264): the stable reorder into buffer 2.
+int sort_reorder_phase(wc_handle* h, bool timed, int n_in, int n_sorted) {
+    const int G = h->p.grid_res;
+    const float bin = h->d.bin_size;
+    int rc;
+    if (n_in > 0 && n_sorted > 0) {
+        k_scatter_ids<<<div_up(n_in, 256), 256, 0, h->stream>>>(h->cell_ids, h->ranks, h->offsets,
+                                                                 n_in, h->ids, (uint32_t)h->Cg);
         WC_CHECK_LAUNCH(h);
-        k_reorder<<<div_up(n, 256), 256, 0, h->stream>>>(h->ids, h->offsets, n, bin, G, h->pos[0],
-                                                          h->vel[0], h->pos[1], h->vel[1],
-                                                          h->perm);
+        k_reorder<<<div_up(n_sorted, 256), 256, 0, h->stream>>>(
+            h->ids, h->offsets, n_sorted, bin, G, h->pos[0], h->vel[0], h->pos[1] + h->Cg,
+            h->vel[1] + h->Cg, h->perm, h->zbase, (uint32_t)h->Cg);
         WC_CHECK_LAUNCH(h);
     }
     if (timed && (rc = record(h, 3))) return rc;
     h->sorted_valid = true;
     h->nbr_valid = false;
     return WC_OK;
+}
+
+int run_sort(wc_handle* h, bool timed) {
+    int rc = sort_count_phase(h, timed);
+    if (rc) return rc;
+    return sort_reorder_phase(h, timed, h->n, h->n);
 }
 
 int run_density(wc_handle* h, const wc_step_params& sp) {
@@ -217,15 +289,17 @@ int run_update(wc_handle* h, const wc_step_params& sp, float frame_dt) {
                              : NbrList{nullptr, nullptr, nullptr, 0};
     int rc = (h->p.flags & WC_FLAG_SIMPLE_KERNELS)
                  ? -1
-                 : launch_update_tile(h->pos[1], h->vel[1], h->offsets, c, h->pos[0], h->vel[0],
-                                      dbg ? h->forces : nullptr, list, h->stream);
+                 : launch_update_tile(h->pos[1], h->vel[1], h->offsets, c, h->pos[0] + h->M,
+                                      h->vel[0] + h->M, dbg ? h->forces : nullptr, list,
+                                      h->stream);
     if (rc == -1) {
         if (dbg)
             k_update_v1<true><<<div_up(h->n, 128), 128, 0, h->stream>>>(
-                h->pos[1], h->vel[1], h->offsets, c, h->pos[0], h->vel[0], h->forces);
+                h->pos[1], h->vel[1], h->offsets, c, h->pos[0] + h->M, h->vel[0] + h->M,
+                h->forces);
         else
             k_update_v1<false><<<div_up(h->n, 128), 128, 0, h->stream>>>(
-                h->pos[1], h->vel[1], h->offsets, c, h->pos[0], h->vel[0], nullptr);
+                h->pos[1], h->vel[1], h->offsets, c, h->pos[0] + h->M, h->vel[0] + h->M, nullptr);
     }
     WC_CHECK_LAUNCH(h);
     return WC_OK;
@@ -324,13 +398,33 @@ int wc_create(const wc_params* p, wc_handle** out) {
         return fail(WC_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
                     p->device, prop.major, prop.minor);
 
+    const bool slab = p->slab_ghost_capacity > 0;
+    if (slab) {
+        if (p->slab_z_begin < 0 || p->slab_z_end > p->grid_res || p->slab_z_end <= p->slab_z_begin)
+            return fail(WC_ERR_INVALID, "slab layers [%d, %d) are not inside [0, %d)",
+                        p->slab_z_begin, p->slab_z_end, p->grid_res);
+        if (p->slab_migrant_capacity <= 0)
+            return fail(WC_ERR_INVALID, "slab_migrant_capacity must be positive in slab mode");
+    }
+
     wc_handle* h = new (std::nothrow) wc_handle();
     if (!h) return fail(WC_ERR_INVALID, "out of host memory");
     h->p = *p;
     h->d = d;
     h->n = p->num_particles;
     h->cap = cap;
-    h->num_bins = d.num_bins;
+    h->slab = slab;
+    h->Lz = p->grid_res;
+    if (slab) {
+        h->z_begin = p->slab_z_begin;
+        h->z_end = p->slab_z_end;
+        h->Lz = h->z_end - h->z_begin + 2;
+        h->zbase = h->z_begin - 1;
+        h->M = p->slab_migrant_capacity;
+        h->Cg = p->slab_ghost_capacity;
+    }
+    // bins of the (slab-local) cell table
+    h->num_bins = h->Lz * p->grid_res * p->grid_res;
     if (p->stream) {
         h->stream = (cudaStream_t)p->stream;
     } else {
@@ -343,11 +437,22 @@ int wc_create(const wc_params* p, wc_handle** out) {
     }
 
     const size_t capz = (size_t)cap;
-    const size_t nb = (size_t)d.num_bins;
+    const size_t nb = (size_t)h->num_bins;
+    const size_t G2 = (size_t)p->grid_res * p->grid_res;
+    const size_t in_slots = capz + 2 * (size_t)h->M;    // buffer 1: [M | owned | M]
+    const size_t sorted_slots = capz + 2 * (size_t)h->Cg;  // buffer 2: [Cg | owned | Cg]
+    auto scan_state_bytes = [](size_t elems) {
+        const size_t tiles = (elems + kScanTile - 1) / kScanTile + 1;
+        return (tiles * sizeof(unsigned long long) + 255) / 256 * 256 + 256;
+    };
     const size_t counts_bytes = ((nb + 1) * sizeof(uint32_t) + 255) / 256 * 256;
-    const size_t tiles = (nb + kScanTile - 1) / kScanTile + 1;
-    const size_t status_bytes = (tiles * sizeof(unsigned long long) + 255) / 256 * 256;
+    const size_t status_bytes = scan_state_bytes(nb) - 256;
+    // extra scan states (slab): ghost-low, ghost-high tables; the two migrant compactions
+    const size_t xbytes[4] = {scan_state_bytes(G2), scan_state_bytes(G2), scan_state_bytes(capz),
+                              scan_state_bytes(capz)};
     h->arena_bytes = counts_bytes + status_bytes + 256;
+    const size_t x_off0 = h->arena_bytes;
+    if (slab) h->arena_bytes += xbytes[0] + xbytes[1] + xbytes[2] + xbytes[3] + 256;
 
 #define WC_ALLOC(ptr, bytes)                                                            \
     do {                                                                                \
@@ -359,13 +464,13 @@ int wc_create(const wc_params* p, wc_handle** out) {
         }                                                                               \
     } while (0)
 
-    for (int b = 0; b < 2; b++) {
-        WC_ALLOC(h->pos[b], capz * sizeof(float4));
-        WC_ALLOC(h->vel[b], capz * sizeof(float4));
-    }
+    WC_ALLOC(h->pos[0], in_slots * sizeof(float4));
+    WC_ALLOC(h->vel[0], in_slots * sizeof(float4));
+    WC_ALLOC(h->pos[1], sorted_slots * sizeof(float4));
+    WC_ALLOC(h->vel[1], sorted_slots * sizeof(float4));
     WC_ALLOC(h->aos, capz * 2 * sizeof(float4));
-    WC_ALLOC(h->cell_ids, capz * sizeof(uint32_t));
-    WC_ALLOC(h->ranks, capz * sizeof(uint32_t));
+    WC_ALLOC(h->cell_ids, in_slots * sizeof(uint32_t));
+    WC_ALLOC(h->ranks, in_slots * sizeof(uint32_t));
     WC_ALLOC(h->ids, capz * sizeof(uint32_t));
     WC_ALLOC(h->perm, capz * sizeof(uint32_t));
     WC_ALLOC(h->offsets, (nb + 1) * sizeof(uint32_t));
@@ -381,15 +486,46 @@ int wc_create(const wc_params* p, wc_handle** out) {
         WC_ALLOC(h->neighbour_counts, capz * sizeof(uint32_t));
         WC_ALLOC(h->forces, capz * sizeof(float4));
     }
-#undef WC_ALLOC
     h->counts = (uint32_t*)h->arena;
     h->scan_status = (unsigned long long*)((char*)h->arena + counts_bytes);
     h->scan_counter = (unsigned int*)((char*)h->arena + counts_bytes + status_bytes);
-
-    for (int b = 0; b < 2; b++) {
-        cudaMemsetAsync(h->pos[b], 0, capz * sizeof(float4), h->stream);
-        cudaMemsetAsync(h->vel[b], 0, capz * sizeof(float4), h->stream);
+    if (slab) {
+        size_t off = x_off0;
+        for (int k = 0; k < 4; k++) {
+            h->scan_status_x[k] = (unsigned long long*)((char*)h->arena + off);
+            h->scan_counter_x[k] = (unsigned int*)((char*)h->arena + off + xbytes[k] - 256);
+            off += xbytes[k];
+        }
+        h->m_in = (uint32_t*)((char*)h->arena + off);
+        h->info_dev = h->m_in + 8;
+        h->mig_bytes = (size_t)(kMigHeaderFloat4 + 2 * (size_t)h->M) * sizeof(float4);
+        h->lc_bytes = (1 + G2) * sizeof(uint32_t);
+        for (int k = 0; k < 2; k++) {
+            WC_ALLOC(h->mig_out[k], h->mig_bytes);
+            WC_ALLOC(h->mig_in[k], h->mig_bytes);
+            WC_ALLOC(h->lc_send[k], h->lc_bytes);
+            WC_ALLOC(h->lc_recv[k], h->lc_bytes);
+            cudaMemsetAsync(h->mig_out[k], 0, h->mig_bytes, h->stream);
+            cudaMemsetAsync(h->mig_in[k], 0, h->mig_bytes, h->stream);
+            cudaMemsetAsync(h->lc_send[k], 0, h->lc_bytes, h->stream);
+            cudaMemsetAsync(h->lc_recv[k], 0, h->lc_bytes, h->stream);
+        }
+        WC_ALLOC(h->flags, 2 * capz * sizeof(uint32_t));
+        WC_ALLOC(h->slots, 2 * (capz + 1) * sizeof(uint32_t));
+        WC_ALLOC(h->errors, 256);
+        cudaMemsetAsync(h->errors, 0, 256, h->stream);
+        e = cudaMallocHost((void**)&h->info_host, 64);
+        if (e != cudaSuccess) {
+            wc_destroy(h);
+            return fail(WC_ERR_CUDA, "cudaMallocHost: %s", cudaGetErrorString(e));
+        }
     }
+
+#undef WC_ALLOC
+    cudaMemsetAsync(h->pos[0], 0, in_slots * sizeof(float4), h->stream);
+    cudaMemsetAsync(h->vel[0], 0, in_slots * sizeof(float4), h->stream);
+    cudaMemsetAsync(h->pos[1], 0, sorted_slots * sizeof(float4), h->stream);
+    cudaMemsetAsync(h->vel[1], 0, sorted_slots * sizeof(float4), h->stream);
     cudaMemsetAsync(h->offsets, 0, (nb + 1) * sizeof(uint32_t), h->stream);
     cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream);
     if (p->flags & WC_FLAG_STAGE_TIMING) {
@@ -430,6 +566,16 @@ int wc_destroy(wc_handle* h) {
     cudaFree(h->nbr_idx);
     cudaFree(h->nbr_mask);
     cudaFree(h->nbr_words);
+    for (int k = 0; k < 2; k++) {
+        cudaFree(h->mig_out[k]);
+        cudaFree(h->mig_in[k]);
+        cudaFree(h->lc_send[k]);
+        cudaFree(h->lc_recv[k]);
+    }
+    cudaFree(h->flags);
+    cudaFree(h->slots);
+    cudaFree(h->errors);
+    if (h->info_host) cudaFreeHost(h->info_host);
     for (int i = 0; i <= WC_NUM_STAGES; i++)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -449,10 +595,13 @@ static int upload_into(wc_handle* h, int buf, const wc_particle* host_aos, int32
     if (n > h->cap) return fail(WC_ERR_CAPACITY, "n = %d exceeds capacity %d", n, h->cap);
     WC_CUDA(cudaSetDevice(h->p.device));
     h->n = n;
+    if (buf == 0) h->n_in_old = n;
     if (n > 0) {
         WC_CUDA(cudaMemcpyAsync(h->aos, host_aos, (size_t)n * sizeof(wc_particle),
                                 cudaMemcpyHostToDevice, h->stream));
-        wc::k_aos_to_soa<<<div_up(n, 256), 256, 0, h->stream>>>(h->aos, n, h->pos[buf], h->vel[buf]);
+        const int first = buf == 0 ? h->M : h->Cg;  // owned region of buffer 1 / buffer 2
+        wc::k_aos_to_soa<<<div_up(n, 256), 256, 0, h->stream>>>(h->aos, n, h->pos[buf] + first,
+                                                              h->vel[buf] + first);
         WC_CHECK_LAUNCH(h);
     }
     return WC_OK;
@@ -475,8 +624,9 @@ int wc_export_aos_device(wc_handle* h, int32_t which, void* device_dst) {
     if (which != 1 && which != 2) return fail(WC_ERR_INVALID, "which must be 1 or 2");
     WC_CUDA(cudaSetDevice(h->p.device));
     if (h->n > 0) {
+        const int first = which == 1 ? h->M : h->Cg;
         wc::k_soa_to_aos<<<div_up(h->n, 256), 256, 0, h->stream>>>(
-            h->pos[which - 1], h->vel[which - 1], h->n, (float4*)device_dst);
+            h->pos[which - 1] + first, h->vel[which - 1] + first, h->n, (float4*)device_dst);
         WC_CHECK_LAUNCH(h);
     }
     return WC_OK;
@@ -497,6 +647,7 @@ int wc_step(wc_handle* h, float frame_dt, const wc_step_params* sp) {
     if (!h) return fail(WC_ERR_INVALID, "handle is NULL");
     int rc = check_step_params(sp);
     if (rc) return rc;
+    if (h->slab) return fail(WC_ERR_INVALID, "slab handle: use the wc_slab_* sequence");
     WC_CUDA(cudaSetDevice(h->p.device));
     if ((rc = run_sort(h, true))) return rc;          // Fluid.cpp:347
     if ((rc = run_density(h, *sp))) return rc;        // Fluid.cpp:349
@@ -509,6 +660,7 @@ int wc_step(wc_handle* h, float frame_dt, const wc_step_params* sp) {
 
 int wc_sort_only(wc_handle* h) {
     if (!h) return fail(WC_ERR_INVALID, "handle is NULL");
+    if (h->slab) return fail(WC_ERR_INVALID, "slab handle: use the wc_slab_* sequence");
     WC_CUDA(cudaSetDevice(h->p.device));
     h->have_times = false;
     return run_sort(h, false);
@@ -538,21 +690,30 @@ int wc_download_cells(wc_handle* h, uint32_t* cell_ids, uint32_t* counts, uint32
                       uint32_t* sorted_perm, uint32_t* neighbour_counts) {
     if (!h) return fail(WC_ERR_INVALID, "handle is NULL");
     WC_CUDA(cudaSetDevice(h->p.device));
-    const size_t n = (size_t)h->n, nb = (size_t)h->num_bins;
+    const size_t n = (size_t)h->n;
+    const size_t G2 = (size_t)h->p.grid_res * h->p.grid_res;
+    // slab mode: the owned layers only (skip the ghost-low layer), offsets relative to the
+    // first owned slot; cell ids refer to the virtual input and are not exported.
+    const size_t skip = h->slab ? G2 : 0, nb = (size_t)h->num_bins - 2 * skip;
     if (neighbour_counts && !h->neighbour_counts)
         return fail(WC_ERR_INVALID, "neighbour counts need WC_FLAG_DEBUG_OUTPUTS");
+    if (cell_ids && h->slab) return fail(WC_ERR_INVALID, "cell_ids are not exported in slab mode");
     if (cell_ids && n)
         WC_CUDA(cudaMemcpyAsync(cell_ids, h->cell_ids, n * 4, cudaMemcpyDeviceToHost, h->stream));
     if (counts)
-        WC_CUDA(cudaMemcpyAsync(counts, h->counts, nb * 4, cudaMemcpyDeviceToHost, h->stream));
+        WC_CUDA(cudaMemcpyAsync(counts, h->counts + skip, nb * 4, cudaMemcpyDeviceToHost,
+                                h->stream));
     if (offsets)
-        WC_CUDA(cudaMemcpyAsync(offsets, h->offsets, nb * 4, cudaMemcpyDeviceToHost, h->stream));
+        WC_CUDA(cudaMemcpyAsync(offsets, h->offsets + skip, nb * 4, cudaMemcpyDeviceToHost,
+                                h->stream));
     if (sorted_perm && n)
         WC_CUDA(cudaMemcpyAsync(sorted_perm, h->perm, n * 4, cudaMemcpyDeviceToHost, h->stream));
     if (neighbour_counts && n)
         WC_CUDA(cudaMemcpyAsync(neighbour_counts, h->neighbour_counts, n * 4,
                                 cudaMemcpyDeviceToHost, h->stream));
     WC_CUDA(cudaStreamSynchronize(h->stream));
+    if (offsets && h->slab)
+        for (size_t b = 0; b < nb; b++) offsets[b] -= (uint32_t)h->Cg;
     return WC_OK;
 }
 
@@ -602,6 +763,142 @@ int wc_sync(wc_handle* h) {
     if (!h) return fail(WC_ERR_INVALID, "handle is NULL");
     WC_CUDA(cudaSetDevice(h->p.device));
     WC_CUDA(cudaStreamSynchronize(h->stream));
+    return WC_OK;
+}
+
+// ---------------------------------------------------------------------------- z-slab mode
+#define WC_NEED_SLAB(h)                                                         \
+    do {                                                                        \
+        if (!(h)) return fail(WC_ERR_INVALID, "handle is NULL");                \
+        if (!(h)->slab) return fail(WC_ERR_INVALID, "not a slab handle");       \
+        WC_CUDA(cudaSetDevice((h)->p.device));                                  \
+    } while (0)
+
+int wc_slab_get_view(wc_handle* h, wc_slab_view* v) {
+    if (!v) return fail(WC_ERR_INVALID, "NULL argument");
+    WC_NEED_SLAB(h);
+    for (int k = 0; k < 2; k++) {
+        v->mig_out[k] = h->mig_out[k];
+        v->mig_in[k] = h->mig_in[k];
+        v->lc_send[k] = h->lc_send[k];
+        v->lc_recv[k] = h->lc_recv[k];
+    }
+    v->pos_rho_sorted = h->pos[1];
+    v->vel_pres_sorted = h->vel[1];
+    v->mig_bytes = h->mig_bytes;
+    v->lc_bytes = h->lc_bytes;
+    v->owned_first = h->Cg;
+    v->reserved = 0;
+    return WC_OK;
+}
+
+int wc_slab_clear_recv(wc_handle* h, int32_t direction) {
+    WC_NEED_SLAB(h);
+    if (direction != 0 && direction != 1) return fail(WC_ERR_INVALID, "direction must be 0 or 1");
+    WC_CUDA(cudaMemsetAsync(h->mig_in[direction], 0, 32, h->stream));
+    WC_CUDA(cudaMemsetAsync(h->lc_recv[direction], 0, h->lc_bytes, h->stream));
+    return WC_OK;
+}
+
+int wc_slab_sort_count(wc_handle* h) {
+    WC_NEED_SLAB(h);
+    h->have_times = false;
+    return sort_count_phase(h, true);
+}
+
+int wc_slab_sync_info(wc_handle* h, int32_t info[8]) {
+    if (!info) return fail(WC_ERR_INVALID, "NULL argument");
+    WC_NEED_SLAB(h);
+    uint32_t* hi = h->info_host;
+    WC_CUDA(cudaMemcpyAsync(hi, h->info_dev, 12, cudaMemcpyDeviceToHost, h->stream));
+    WC_CUDA(cudaMemcpyAsync(hi + 3, h->lc_recv[0], 4, cudaMemcpyDeviceToHost, h->stream));
+    WC_CUDA(cudaMemcpyAsync(hi + 4, h->lc_recv[1], 4, cudaMemcpyDeviceToHost, h->stream));
+    WC_CUDA(cudaMemcpyAsync(hi + 5, h->errors, 4, cudaMemcpyDeviceToHost, h->stream));
+    WC_CUDA(cudaMemcpyAsync(hi + 6, h->m_in, 8, cudaMemcpyDeviceToHost, h->stream));
+    WC_CUDA(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 8; k++) info[k] = (int32_t)hi[k];
+    if ((int)hi[0] > h->cap)
+        return fail(WC_ERR_CAPACITY, "slab holds %u particles, capacity %d", hi[0], h->cap);
+    if ((int)hi[3] > h->Cg || (int)hi[4] > h->Cg)
+        return fail(WC_ERR_CAPACITY, "halo layer of %u / %u particles exceeds slab_ghost_capacity %d",
+                    hi[3], hi[4], h->Cg);
+    h->n = (int)hi[0];
+    h->n_first = (int)hi[1];
+    h->n_last = (int)hi[2];
+    h->n_glow = (int)hi[3];
+    h->n_ghigh = (int)hi[4];
+    h->info_valid = true;
+    return WC_OK;
+}
+
+int wc_slab_reorder(wc_handle* h) {
+    WC_NEED_SLAB(h);
+    if (!h->info_valid) return fail(WC_ERR_INVALID, "wc_slab_reorder needs wc_slab_sync_info");
+    const int G2 = h->p.grid_res * h->p.grid_res;
+    // ghost layers: the neighbours' counts, scanned so the halo slices sit right before /
+    // after the owned slice: [Cg - n_glow, Cg) and [Cg + n, Cg + n + n_ghigh)
+    k_install_ghost_counts<<<div_up(G2, 256), 256, 0, h->stream>>>(h->lc_recv[0], h->lc_recv[1], G2,
+                                                                  h->Lz, h->counts);
+    WC_CHECK_LAUNCH(h);
+    k_scan<<<div_up(G2, kScanTile), kScanThreads, 0, h->stream>>>(
+        h->counts, h->offsets, G2, h->scan_status_x[0], h->scan_counter_x[0],
+        (uint32_t)(h->Cg - h->n_glow));
+    WC_CHECK_LAUNCH(h);
+    k_scan<<<div_up(G2, kScanTile), kScanThreads, 0, h->stream>>>(
+        h->counts + (size_t)(h->Lz - 1) * G2, h->offsets + (size_t)(h->Lz - 1) * G2, G2,
+        h->scan_status_x[1], h->scan_counter_x[1], (uint32_t)(h->Cg + h->n));
+    WC_CHECK_LAUNCH(h);
+    // the virtual input still has the OLD owned count between the migrant slots
+    const int n_in = h->M + h->n_in_old + h->M;
+    return sort_reorder_phase(h, true, n_in, h->n);
+}
+
+int wc_slab_density(wc_handle* h, const wc_step_params* sp) {
+    WC_NEED_SLAB(h);
+    int rc = check_step_params(sp);
+    if (rc) return rc;
+    if (!h->sorted_valid) return fail(WC_ERR_INVALID, "wc_slab_density needs wc_slab_reorder");
+    if ((rc = run_density(h, *sp))) return rc;
+    return record(h, 4);
+}
+
+int wc_slab_update(wc_handle* h, float frame_dt, const wc_step_params* sp) {
+    WC_NEED_SLAB(h);
+    int rc = check_step_params(sp);
+    if (rc) return rc;
+    if (!h->sorted_valid) return fail(WC_ERR_INVALID, "wc_slab_update needs wc_slab_reorder");
+    const float bin = h->d.bin_size;
+    if (!(50.0f * fabsf(frame_dt * h->p.time_scale) < bin))
+        return fail(WC_ERR_INVALID, "dt too large for one-layer migration: 50 * dt >= binSize");
+    if ((rc = run_update(h, *sp, frame_dt))) return rc;
+    // Particles whose new z-layer left the slab: only the first / last owned layer can lose
+    // any (|v| dt < binSize), and those layers are the head / tail of the sorted order.
+    const int G = h->p.grid_res;
+    const float4* own_pos = h->pos[0] + h->M;
+    const float4* own_vel = h->vel[0] + h->M;
+    for (int dir = 0; dir < 2; dir++) {
+        const int n_layer = dir == 0 ? h->n_first : h->n_last;
+        const int start = dir == 0 ? 0 : h->n - h->n_last;
+        uint32_t* flags = h->flags + (size_t)dir * h->cap;
+        uint32_t* slots = h->slots + (size_t)dir * (h->cap + 1);
+        if (n_layer > 0) {
+            k_flag_migrants<<<div_up(n_layer, 256), 256, 0, h->stream>>>(
+                own_pos + start, n_layer, bin, G, dir == 0 ? h->z_begin : h->z_end, dir, flags);
+            WC_CHECK_LAUNCH(h);
+        }
+        const int scan_blocks = n_layer > 0 ? div_up(n_layer, kScanTile) : 1;
+        k_scan<<<scan_blocks, kScanThreads, 0, h->stream>>>(flags, slots, n_layer,
+                                                            h->scan_status_x[2 + dir],
+                                                            h->scan_counter_x[2 + dir], 0u);
+        WC_CHECK_LAUNCH(h);
+        k_pack_migrants<<<div_up(n_layer > 0 ? n_layer : 1, 256), 256, 0, h->stream>>>(
+            own_pos + start, own_vel + start, n_layer, flags, slots, h->M, h->mig_out[dir],
+            h->errors);
+        WC_CHECK_LAUNCH(h);
+    }
+    h->n_in_old = h->n;
+    if ((rc = record(h, 5))) return rc;
+    h->have_times = (h->p.flags & WC_FLAG_STAGE_TIMING) != 0;
     return WC_OK;
 }
 

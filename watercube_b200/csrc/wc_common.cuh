@@ -11,8 +11,11 @@ constexpr int kWarp = 32;
 // Everything the density / update kernels read as GLSL uniforms
 // (src/core/Fluid.cpp:276-285, :305-317), plus values precomputed once on the host.
 struct SphConsts {
-    int n;           // numParticles
+    int n;           // numParticles (targets of this launch)
+    int first;       // index of the first target in the candidate arrays (0 unless slab mode)
     int G;           // gridRes
+    int Gz;          // z-layers covered by the offsets table (G, or slab layers + 2 ghost layers)
+    int zbase;       // global z-layer of the table's layer 0 (0, or slab z_begin - 1)
     float bin;       // binSize
     float size;      // size
     float h;         // kernelRadius
@@ -37,11 +40,12 @@ __device__ __forceinline__ int cell_coord(float p, float bin, int G) {
     return __float2int_rz(q);
 }
 
-// count.comp:33
-__device__ __forceinline__ uint32_t cell_index(float x, float y, float z, float bin, int G) {
+// count.comp:33.  zbase shifts the z-layer for a slab-local table (0 for the whole grid).
+__device__ __forceinline__ uint32_t cell_index(float x, float y, float z, float bin, int G,
+                                               int zbase = 0) {
     const uint32_t cx = (uint32_t)cell_coord(x, bin, G);
     const uint32_t cy = (uint32_t)cell_coord(y, bin, G);
-    const uint32_t cz = (uint32_t)cell_coord(z, bin, G);
+    const uint32_t cz = (uint32_t)(cell_coord(z, bin, G) - zbase);
     return (cz * (uint32_t)G + cy) * (uint32_t)G + cx;
 }
 

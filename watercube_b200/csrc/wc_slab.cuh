@@ -1,0 +1,134 @@
+// wc_slab.cuh -- device pieces of the z-slab decomposition (multi-GPU).
+//
+// The reference is single-GPU; this is new work.  The cell index is z-major
+// (count.comp:33), so a rank that owns z-layers [z_begin, z_end) owns a contiguous range of
+// bins and, after the sort, a contiguous slice of the particle array; its first / last
+// layer (the halo the neighbours need) are contiguous sub-slices, so halo sends need no
+// packing.  Layout on one rank (slab-local table of z_end - z_begin + 2 layers):
+//
+//   buffer 1 (input):   [ M slots: migrants from below | owned, previous order | M: from above ]
+//   buffer 2 (sorted):  [ ... ghost-low layer ][ owned, cell-sorted ][ ghost-high layer ... ]
+//                                             ^ index Cg
+// Concatenating the ranks' inputs in z order reproduces the single-GPU input order for every
+// cell (particles that arrive from the rank below come first, from above last), so the stable
+// sort -- and with it every result -- is bit-identical to the undecomposed run.
+#pragma once
+
+#include "wc_common.cuh"
+
+namespace wc {
+
+constexpr int kMigHeaderFloat4 = 2;  // 32-byte message header: [count, 7 x pad]
+
+// Incoming migrant message (header + AoS payload) -> SoA slots of buffer 1.
+__global__ void k_unpack_migrants(const float4* __restrict__ msg, int cap,
+                                  float4* __restrict__ pos_dst, float4* __restrict__ vel_dst,
+                                  uint32_t* __restrict__ count_out) {
+    const uint32_t count = min(reinterpret_cast<const uint32_t*>(msg)[0], (uint32_t)cap);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *count_out = count;
+    if ((uint32_t)i >= count) return;
+    pos_dst[i] = msg[kMigHeaderFloat4 + 2 * (size_t)i];
+    vel_dst[i] = msg[kMigHeaderFloat4 + 2 * (size_t)i + 1];
+}
+
+// count.comp:25-36 over the virtual input [from-below | owned | from-above].  A slot takes
+// part when it holds a received migrant, or an owned particle that is still inside the slab
+// (owned particles that left were sent to the neighbour at the end of the previous step).
+__global__ void __launch_bounds__(256)
+k_hash_count_slab(const float4* __restrict__ pos, int total, int M, int n_old,
+                  const uint32_t* __restrict__ m_in, float bin, int G, int z_begin, int z_end,
+                  uint32_t* __restrict__ cell_ids, uint32_t* __restrict__ ranks,
+                  uint32_t* __restrict__ counts, uint32_t* __restrict__ errors) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < total;
+    uint32_t c = 0xFFFFFFFFu;
+    if (active) {
+        const bool own = i >= M && i < M + n_old;
+        const bool valid = own || (i < M ? (uint32_t)i < m_in[0] : (uint32_t)(i - M - n_old) < m_in[1]);
+        if (valid) {
+            const float4 p = pos[i];
+            const int cz = cell_coord(p.z, bin, G);
+            if (cz >= z_begin && cz < z_end) {
+                c = cell_index(p.x, p.y, p.z, bin, G, z_begin - 1);
+            } else if (!own) {
+                atomicAdd(errors, 1u);  // a migrant that is not ours: moved more than one layer
+            }
+        }
+    }
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned group = __match_any_sync(0xffffffffu, c);
+    if (active) {
+        cell_ids[i] = c;
+        if (c != 0xFFFFFFFFu) {
+            const int leader = __ffs(group) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(&counts[c], (uint32_t)__popc(group));
+            base = __shfl_sync(group, base, leader);
+            ranks[i] = base + (uint32_t)__popc(group & ((1u << lane) - 1u));
+        }
+    }
+}
+
+// After the owned-layer scan: counts of the slab and its boundary layers, and the
+// layer-count messages [n_layer, counts of the layer's G*G cells] for the two neighbours.
+__global__ void k_slab_info(const uint32_t* __restrict__ counts,
+                            const uint32_t* __restrict__ offsets, int G2, int Lz, uint32_t Cg,
+                            uint32_t* __restrict__ info, uint32_t* __restrict__ lc_down,
+                            uint32_t* __restrict__ lc_up) {
+    const uint32_t n_own = offsets[(size_t)(Lz - 1) * G2] - Cg;
+    const uint32_t n_first = offsets[(size_t)2 * G2] - Cg;
+    const uint32_t n_last = n_own - (offsets[(size_t)(Lz - 2) * G2] - Cg);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        info[0] = n_own, info[1] = n_first, info[2] = n_last;
+        lc_down[0] = n_first;
+        lc_up[0] = n_last;
+    }
+    if (i < G2) {
+        lc_down[1 + i] = counts[(size_t)G2 + i];
+        lc_up[1 + i] = counts[(size_t)(Lz - 2) * G2 + i];
+    }
+}
+
+// Received layer counts -> the table's ghost layers.
+__global__ void k_install_ghost_counts(const uint32_t* __restrict__ lc_below,
+                                       const uint32_t* __restrict__ lc_above, int G2, int Lz,
+                                       uint32_t* __restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G2) return;
+    counts[i] = lc_below[1 + i];
+    counts[(size_t)(Lz - 1) * G2 + i] = lc_above[1 + i];
+}
+
+// End of step: particles of the first / last owned layer whose new z-layer left the slab.
+// dir 0: below z_begin (go to rank - 1); dir 1: at or above z_end (go to rank + 1).
+__global__ void k_flag_migrants(const float4* __restrict__ pos, int n, float bin, int G,
+                                int z_limit, int dir, uint32_t* __restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cz = cell_coord(pos[i].z, bin, G);
+    flags[i] = (dir == 0 ? cz < z_limit : cz >= z_limit) ? 1u : 0u;
+}
+
+// Stable compaction (order preserved: see the file comment) into the outgoing message.
+__global__ void k_pack_migrants(const float4* __restrict__ pos, const float4* __restrict__ vel,
+                                int n, const uint32_t* __restrict__ flags,
+                                const uint32_t* __restrict__ slot, int cap,
+                                float4* __restrict__ msg, uint32_t* __restrict__ errors) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        const uint32_t total = slot[n];
+        reinterpret_cast<uint32_t*>(msg)[0] = min(total, (uint32_t)cap);
+        if (total > (uint32_t)cap) atomicAdd(errors, total - (uint32_t)cap);
+    }
+    if (i >= n || !flags[i]) return;
+    const uint32_t s = slot[i];
+    if (s >= (uint32_t)cap) return;
+    msg[kMigHeaderFloat4 + 2 * (size_t)s] = pos[i];
+    msg[kMigHeaderFloat4 + 2 * (size_t)s + 1] = vel[i];
+}
+
+__global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
+
+}  // namespace wc

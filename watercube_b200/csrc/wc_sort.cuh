@@ -79,10 +79,11 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
     *reinterpret_cast<volatile unsigned long long*>(p) = v;
 }
 
-// Writes out[i] = sum(in[0..i)) for i < n and out[n] = sum(in[0..n)).
+// Writes out[i] = out_base + sum(in[0..i)) for i < n and out[n] = out_base + sum(in[0..n)).
 __global__ void __launch_bounds__(kScanThreads)
 k_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n,
-       unsigned long long* __restrict__ status, unsigned int* __restrict__ tile_counter) {
+       unsigned long long* __restrict__ status, unsigned int* __restrict__ tile_counter,
+       uint32_t out_base) {
     __shared__ unsigned int s_tile;
     __shared__ uint32_t s_warp[kScanThreads / kWarp];
     __shared__ uint32_t s_prefix;
@@ -155,25 +156,30 @@ k_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n,
     }
     __syncthreads();
 
-    uint32_t run = s_prefix + s_warp[warp] + (incl - tsum);
+    uint32_t run = out_base + s_prefix + s_warp[warp] + (incl - tsum);
 #pragma unroll
     for (int k = 0; k < kScanItems; k++) {
         if (base + k < n) out[base + k] = run;
         run += v[k];
         if (base + k == n - 1) out[n] = run;
     }
-    if (n == 0 && tile == 0 && tid == 0) out[0] = 0;
+    if (n == 0 && tile == 0 && tid == 0) out[0] = out_base;
 }
 
 // ---------------------------------------------------------------------------------------
 // sort.comp:41-44: sorted[offsets[cell] + localOffset] = particleID, with the arrival rank
 // recorded by k_hash_count standing in for the second atomicAdd pass.
+// `base` is the index the offsets table assigns to the first sorted slot (0 unless slab
+// mode); cell id 0xFFFFFFFF marks an input slot that does not take part (slab mode).
 __global__ void __launch_bounds__(256)
 k_scatter_ids(const uint32_t* __restrict__ cell_ids, const uint32_t* __restrict__ ranks,
-              const uint32_t* __restrict__ offsets, int n, uint32_t* __restrict__ ids) {
+              const uint32_t* __restrict__ offsets, int n, uint32_t* __restrict__ ids,
+              uint32_t base) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    ids[offsets[cell_ids[i]] + ranks[i]] = (uint32_t)i;
+    const uint32_t c = cell_ids[i];
+    if (c == 0xFFFFFFFFu) return;
+    ids[offsets[c] - base + ranks[i]] = (uint32_t)i;
 }
 
 // reorder.comp:32-45 made stable.  One thread per slot j of the arrival-ordered ID list:
@@ -185,14 +191,14 @@ __global__ void __launch_bounds__(256)
 k_reorder(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ offsets, int n, float bin,
           int G, const float4* __restrict__ pos_in, const float4* __restrict__ vel_in,
           float4* __restrict__ pos_out, float4* __restrict__ vel_out,
-          uint32_t* __restrict__ perm) {
+          uint32_t* __restrict__ perm, int zbase, uint32_t base) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const uint32_t id = ids[j];
     const float4 p = pos_in[id];
     const float4 v = vel_in[id];
-    const uint32_t c = cell_index(p.x, p.y, p.z, bin, G);
-    const uint32_t beg = offsets[c], end = offsets[c + 1];
+    const uint32_t c = cell_index(p.x, p.y, p.z, bin, G, zbase);
+    const uint32_t beg = offsets[c] - base, end = offsets[c + 1] - base;
     uint32_t rank = 0;
     for (uint32_t k = beg; k < end; k++) rank += (ids[k] < id) ? 1u : 0u;
     const uint32_t dst = beg + rank;

@@ -195,7 +195,7 @@ __device__ __forceinline__ void gather_rows(const float4* pos_rho, const float4*
     int cx = 0, cy = 0, cz = 0, row = -1;
     if (valid) {
         cx = cell_coord(p.x, c.bin, G), cy = cell_coord(p.y, c.bin, G),
-        cz = cell_coord(p.z, c.bin, G);
+        cz = cell_coord(p.z, c.bin, G) - c.zbase;
         row = cz * G + cy;
     }
     const float Tcull = c.T * 1.0001f;  // conservative: rounding in the box distance
@@ -224,7 +224,7 @@ __device__ __forceinline__ void gather_rows(const float4* pos_rho, const float4*
         uint32_t sbeg = 0, send = 0;
         if (lane < 9) {
             const int z = rz + lane / 3 - 1, y = ry + lane % 3 - 1;
-            if (z >= 0 && z < G && y >= 0 && y < G) {
+            if (z >= 0 && z < c.Gz && y >= 0 && y < G) {
                 const uint32_t rowbase = ((uint32_t)z * G + (uint32_t)y) * G;
                 sbeg = offsets[rowbase + x0];
                 send = offsets[rowbase + x1 + 1];
@@ -312,8 +312,9 @@ k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
     __shared__ DensityStage s_stage[kTileWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wg = blockIdx.x * kTileWarps + warp;
-    const int i = wg * 32 + lane;
-    const bool valid = i < c.n;
+    const int t = wg * 32 + lane;         // target number within this launch
+    const int i = c.first + t;            // its index in the candidate arrays
+    const bool valid = t < c.n;
     float4 p = make_float4(0, 0, 0, 0);
     if (valid) p = pos_rho[i];
     DensityAcc<kDebug> acc;
@@ -332,7 +333,7 @@ k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
     // In place like density.comp:135; the gather only reads x,y,z, which do not change.
     reinterpret_cast<float*>(pos_rho)[4 * (size_t)i + 3] = rho;
     reinterpret_cast<float*>(vel_pres)[4 * (size_t)i + 3] = pres;
-    if (kDebug) neighbour_counts[i] = acc.nn;  // the self pair's bit is already cleared
+    if (kDebug) neighbour_counts[t] = acc.nn;  // the self pair's bit is already cleared
 }
 
 // update.comp:134-232.  With a valid neighbour list the warp replays the density pass's
@@ -346,8 +347,9 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
     __shared__ UpdateStage s_stage[kTileWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wg = blockIdx.x * kTileWarps + warp;
-    const int i = wg * 32 + lane;
-    const bool valid = i < c.n;
+    const int t = wg * 32 + lane;
+    const int i = c.first + t;
+    const bool valid = t < c.n;
     float4 p = make_float4(0, 0, 0, 0), v = make_float4(0, 0, 0, 0);
     if (valid) {
         p = pos_rho[i];
@@ -394,9 +396,9 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
     float4 po, vo, fo;
     integrate(c, p, v, acc.Fpx * kp, acc.Fpy * kp, acc.Fpz * kp, acc.Fvx * kv, acc.Fvy * kv,
               acc.Fvz * kv, &po, &vo, kDebug ? &fo : nullptr);
-    pos_out[i] = po;
-    vel_out[i] = vo;
-    if (kDebug) forces[i] = fo;
+    pos_out[t] = po;
+    vel_out[t] = vo;
+    if (kDebug) forces[t] = fo;
 }
 
 inline int tile_blocks(int n) { return (n + kTileWarps * 32 - 1) / (kTileWarps * 32); }

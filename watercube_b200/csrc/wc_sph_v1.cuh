@@ -125,18 +125,19 @@ template <bool kDebug>
 __global__ void __launch_bounds__(128)
 k_density_v1(float4* pos_rho, float4* __restrict__ vel_pres, const uint32_t* __restrict__ offsets,
              SphConsts c, uint32_t* __restrict__ neighbour_counts) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= c.n) return;
+    const int i = c.first + t;
     const float4 p = pos_rho[i];
     const int G = c.G;
     const int cx = cell_coord(p.x, c.bin, G), cy = cell_coord(p.y, c.bin, G),
-              cz = cell_coord(p.z, c.bin, G);
+              cz = cell_coord(p.z, c.bin, G) - c.zbase;
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, G - 1);
     float acc = 0.0f;
     uint32_t nn = 0;
     for (int dz = -1; dz <= 1; dz++) {
         const int z = cz + dz;
-        if (z < 0 || z >= G) continue;
+        if (z < 0 || z >= c.Gz) continue;
         for (int dy = -1; dy <= 1; dy++) {
             const int y = cy + dy;
             if (y < 0 || y >= G) continue;
@@ -157,7 +158,7 @@ k_density_v1(float4* pos_rho, float4* __restrict__ vel_pres, const uint32_t* __r
     // In place like density.comp:135; the gather only reads x,y,z, which do not change.
     reinterpret_cast<float*>(pos_rho)[4 * (size_t)i + 3] = rho;
     reinterpret_cast<float*>(vel_pres)[4 * (size_t)i + 3] = pres;
-    if (kDebug) neighbour_counts[i] = nn - 1u;  // the self pair is not a neighbour (j != i)
+    if (kDebug) neighbour_counts[t] = nn - 1u;  // the self pair is not a neighbour (j != i)
 }
 
 template <bool kDebug>
@@ -165,18 +166,19 @@ __global__ void __launch_bounds__(128)
 k_update_v1(const float4* __restrict__ pos_rho, const float4* __restrict__ vel_pres,
             const uint32_t* __restrict__ offsets, SphConsts c, float4* __restrict__ pos_out,
             float4* __restrict__ vel_out, float4* __restrict__ forces) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= c.n) return;
+    const int i = c.first + t;
     const float4 p = pos_rho[i];
     const float4 v = vel_pres[i];
     const int G = c.G;
     const int cx = cell_coord(p.x, c.bin, G), cy = cell_coord(p.y, c.bin, G),
-              cz = cell_coord(p.z, c.bin, G);
+              cz = cell_coord(p.z, c.bin, G) - c.zbase;
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, G - 1);
     float Fpx = 0, Fpy = 0, Fpz = 0, Fvx = 0, Fvy = 0, Fvz = 0;
     for (int dz = -1; dz <= 1; dz++) {
         const int z = cz + dz;
-        if (z < 0 || z >= G) continue;
+        if (z < 0 || z >= c.Gz) continue;
         for (int dy = -1; dy <= 1; dy++) {
             const int y = cy + dy;
             if (y < 0 || y >= G) continue;
@@ -197,9 +199,9 @@ k_update_v1(const float4* __restrict__ pos_rho, const float4* __restrict__ vel_p
     float4 po, vo, fo;
     integrate(c, p, v, Fpx * kp, Fpy * kp, Fpz * kp, Fvx * kv, Fvy * kv, Fvz * kv, &po, &vo,
               kDebug ? &fo : nullptr);
-    pos_out[i] = po;
-    vel_out[i] = vo;
-    if (kDebug) forces[i] = fo;
+    pos_out[t] = po;
+    vel_out[t] = vo;
+    if (kDebug) forces[t] = fo;
 }
 
 }  // namespace wc
