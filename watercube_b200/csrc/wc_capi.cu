@@ -104,6 +104,11 @@ struct wc_handle {
     uint32_t* nbr_words = nullptr;
     int nbr_cap_words = 0;
     bool nbr_valid = false;
+    // group table of the tiled gather kernels (wc_sph_tile.cuh k_build_groups)
+    uint32_t* group_start = nullptr;
+    uint32_t* group_row = nullptr;
+    uint32_t* num_groups = nullptr;
+    int groups_cap = 0;
 
     // Arena cleared once per sort: counts | scan status | scan tile counter.
     void* arena = nullptr;
@@ -245,10 +250,21 @@ int sort_reorder_phase(wc_handle* h, bool timed, int n_in, int n_sorted) {
             h->vel[1] + h->Cg, h->perm, h->zbase, (uint32_t)h->Cg);
         WC_CHECK_LAUNCH(h);
     }
+    if (h->group_start) {  // cut the owned rows into <= 32-particle groups for the gathers
+        const int row0 = h->slab ? G : 0, row1 = h->slab ? (h->Lz - 1) * G : h->Lz * G;
+        k_build_groups<<<1, 1024, 0, h->stream>>>(h->offsets, G, row0, row1, h->group_start,
+                                                  h->group_row, h->num_groups);
+        WC_CHECK_LAUNCH(h);
+    }
     if (timed && (rc = record(h, 3))) return rc;
     h->sorted_valid = true;
     h->nbr_valid = false;
     return WC_OK;
+}
+
+GroupTable group_table(const wc_handle* h) {
+    return GroupTable{h->group_start, h->group_row, h->num_groups,
+                      max_groups(h->n, (long long)h->Lz * h->p.grid_res)};
 }
 
 int run_sort(wc_handle* h, bool timed) {
@@ -262,12 +278,12 @@ int run_density(wc_handle* h, const wc_step_params& sp) {
     const SphConsts c = make_consts(h, sp, 0.0f);
     const bool dbg = h->p.flags & WC_FLAG_DEBUG_OUTPUTS;
     const NbrList list{h->nbr_idx, h->nbr_mask, h->nbr_words, h->nbr_cap_words};
-    int rc = (h->p.flags & WC_FLAG_SIMPLE_KERNELS)
-                 ? -1
-                 : launch_density_tile(h->pos[1], h->vel[1], h->offsets, c,
-                                       dbg ? h->neighbour_counts : nullptr, list, h->stream);
-    h->nbr_valid = (rc == 0) && h->nbr_idx != nullptr;
-    if (rc == -1) {  // geometry the tile kernel does not cover: simple path
+    const bool simple = h->p.flags & WC_FLAG_SIMPLE_KERNELS;
+    if (!simple)
+        launch_density_tile(h->pos[1], h->vel[1], h->offsets, c, group_table(h),
+                            dbg ? h->neighbour_counts : nullptr, list, h->stream);
+    h->nbr_valid = !simple && h->nbr_idx != nullptr;
+    if (simple) {
         if (dbg)
             k_density_v1<true><<<div_up(h->n, 128), 128, 0, h->stream>>>(
                 h->pos[1], h->vel[1], h->offsets, c, h->neighbour_counts);
@@ -287,12 +303,11 @@ int run_update(wc_handle* h, const wc_step_params& sp, float frame_dt) {
     const NbrList list = h->nbr_valid
                              ? NbrList{h->nbr_idx, h->nbr_mask, h->nbr_words, h->nbr_cap_words}
                              : NbrList{nullptr, nullptr, nullptr, 0};
-    int rc = (h->p.flags & WC_FLAG_SIMPLE_KERNELS)
-                 ? -1
-                 : launch_update_tile(h->pos[1], h->vel[1], h->offsets, c, h->pos[0] + h->M,
-                                      h->vel[0] + h->M, dbg ? h->forces : nullptr, list,
-                                      h->stream);
-    if (rc == -1) {
+    const bool simple = h->p.flags & WC_FLAG_SIMPLE_KERNELS;
+    if (!simple)
+        launch_update_tile(h->pos[1], h->vel[1], h->offsets, c, group_table(h), h->pos[0] + h->M,
+                           h->vel[0] + h->M, dbg ? h->forces : nullptr, list, h->stream);
+    if (simple) {
         if (dbg)
             k_update_v1<true><<<div_up(h->n, 128), 128, 0, h->stream>>>(
                 h->pos[1], h->vel[1], h->offsets, c, h->pos[0] + h->M, h->vel[0] + h->M,
@@ -475,12 +490,19 @@ int wc_create(const wc_params* p, wc_handle** out) {
     WC_ALLOC(h->perm, capz * sizeof(uint32_t));
     WC_ALLOC(h->offsets, (nb + 1) * sizeof(uint32_t));
     WC_ALLOC(h->arena, h->arena_bytes);
-    if (p->neighbour_list_words >= 0 && !(p->flags & WC_FLAG_SIMPLE_KERNELS)) {
-        h->nbr_cap_words = p->neighbour_list_words > 0 ? p->neighbour_list_words : 32;
-        const size_t warps = (size_t)tile_warps(cap);
-        WC_ALLOC(h->nbr_idx, warps * h->nbr_cap_words * 32 * sizeof(uint32_t));
-        WC_ALLOC(h->nbr_mask, warps * h->nbr_cap_words * 32 * sizeof(uint32_t));
-        WC_ALLOC(h->nbr_words, warps * sizeof(uint32_t));
+    if (!(p->flags & WC_FLAG_SIMPLE_KERNELS)) {
+        h->groups_cap = max_groups(cap, (long long)h->Lz * p->grid_res);
+        const size_t groups = (size_t)h->groups_cap;
+        WC_ALLOC(h->group_start, groups * sizeof(uint32_t));
+        WC_ALLOC(h->group_row, groups * sizeof(uint32_t));
+        WC_ALLOC(h->num_groups, 256);
+        cudaMemsetAsync(h->num_groups, 0, 256, h->stream);
+        if (p->neighbour_list_words >= 0) {
+            h->nbr_cap_words = p->neighbour_list_words > 0 ? p->neighbour_list_words : 32;
+            WC_ALLOC(h->nbr_idx, groups * h->nbr_cap_words * 32 * sizeof(uint32_t));
+            WC_ALLOC(h->nbr_mask, groups * h->nbr_cap_words * 32 * sizeof(uint32_t));
+            WC_ALLOC(h->nbr_words, groups * sizeof(uint32_t));
+        }
     }
     if (p->flags & WC_FLAG_DEBUG_OUTPUTS) {
         WC_ALLOC(h->neighbour_counts, capz * sizeof(uint32_t));
@@ -566,6 +588,9 @@ int wc_destroy(wc_handle* h) {
     cudaFree(h->nbr_idx);
     cudaFree(h->nbr_mask);
     cudaFree(h->nbr_words);
+    cudaFree(h->group_start);
+    cudaFree(h->group_row);
+    cudaFree(h->num_groups);
     for (int k = 0; k < 2; k++) {
         cudaFree(h->mig_out[k]);
         cudaFree(h->mig_in[k]);

@@ -95,7 +95,10 @@ k_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n,
     const int base = tile * kScanTile + tid * kScanItems;
 
     uint32_t v[kScanItems];
-    if (base + kScanItems <= n) {  // in[] is 256-byte aligned and base is a multiple of 4
+    // base is a multiple of 4; in[] itself is only 16-byte aligned for the whole-grid table
+    // (slab mode scans from counts + G*G, any alignment), so the vector path checks it.
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+    if (vec_ok && base + kScanItems <= n) {
         const uint4 q = *reinterpret_cast<const uint4*>(in + base);
         v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
     } else {

@@ -1,21 +1,28 @@
 // wc_sph_tile.cuh -- warp-cooperative gather kernels for density.comp / update.comp.
 //
-// One warp owns 32 consecutive cell-sorted particles (one per lane).  Because the array is
-// cell-major with x fastest (count.comp:33), the warp's targets that share a (y,z) cell row
-// are consecutive lanes, and their joint 27-cell neighbourhood is nine contiguous slices
-// [offsets[row'+x0], offsets[row'+x1+1]) of the sorted array.  Per row the warp
-//   1. streams each slice once with coalesced float4 loads (32 candidates per iteration),
-//   2. culls every candidate against the bounding box of the row's targets grown by h
-//      (one lane per candidate, ballot-compacted into a per-warp shared-memory stage),
-//   3. runs all 32 targets over the staged survivors with broadcast LDS.128 reads.
-// Compared with the thread-per-particle path this turns ~9x32 uncoalesced table walks into
-// one coalesced stream, and drops about half of the candidates before the per-pair test.
-// The update kernel additionally separates the cheap distance test (phase 1: a bit mask per
-// lane) from the expensive pair force (phase 2: lanes walk their own bits), so the heavy
-// code runs at near-full lane utilisation instead of once per candidate.
+// Work unit: a GROUP = up to 32 consecutive cell-sorted particles of ONE (y,z) cell row (one
+// per lane; k_build_groups cuts every row into such groups).  Because the array is
+// cell-major with x fastest (count.comp:33), the group's joint 27-cell neighbourhood is nine
+// contiguous slices [offsets[row'+x0], offsets[row'+x1+1]) of the sorted array.  Per group
+// the warp
+//   1. streams the nine slices once with coalesced float4 loads (32 candidates per
+//      iteration) and culls every candidate against the bounding box of the group's targets
+//      grown by h (one lane per candidate, ballot-compacted into a per-warp shared-memory
+//      stage in SoA layout),
+//   2. runs all 32 targets over the staged survivors: broadcast LDS.128 reads fetch four
+//      candidates at a time and the distance test runs on sm_100's packed fp32 pipe
+//      (FADD2 / FMUL2 / FFMA2, two candidates per instruction, each half IEEE-rn, so the
+//      result is bit-identical to the oracle's fma(rz,rz,fma(ry,ry,rx*rx))),
+//   3. records, word by word, which 32 staged candidates it looked at and which of them each
+//      lane accepted (the neighbour list), so that
+//   4. the update pass replays the list: it re-stages the listed candidates (position,
+//      1/rho, velocity, pressure) 256 at a time and every lane walks only its own accepted
+//      bits -- no second cull, no second distance test.
+// Row-aligned groups keep the culled candidate set near its floor for 32 shared targets
+// (~500 at the reference's cell geometry instead of ~720 for unaligned 32-particle runs).
 //
-// Summation order differs from the simple path (stage order), so floating-point results
-// agree to rounding, while neighbour counts and all sort outputs stay bit-exact.
+// Summation order differs from the simple path, so floating-point results agree to
+// rounding, while neighbour counts and all sort outputs stay bit-exact.
 #pragma once
 
 #include "wc_common.cuh"
@@ -23,76 +30,236 @@
 
 namespace wc {
 
-constexpr int kTileWarps = 8;              // warps (= 32-target groups) per block
-constexpr int kChunk = 128;                // staged candidates processed per batch
+constexpr int kDensityWarps = 8;           // warps (= groups) per block, density pass
+constexpr int kUpdateWarps = 4;            // warps per block, update pass (10.6 KB stage each)
+constexpr int kChunk = 128;                // staged candidates per density batch (4 words)
 constexpr int kStageCap = kChunk + 32;     // one cull iteration can overshoot by < 32
+constexpr int kReplayWords = 8;            // list words re-staged per update batch
+constexpr int kReplaySlots = kReplayWords * 32;
 constexpr float kFar = 1e18f;              // sentinel coordinate: never within h, no inf/NaN
 
-__device__ __forceinline__ float warp_min_f(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ float warp_max_f(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
-constexpr uint32_t kNoIndex = 0xFFFFFFFFu;     // padding slot in a staged / listed word
+constexpr uint32_t kNoIndex = 0xFFFFFFFFu;       // padding slot in a staged / listed word
 constexpr uint32_t kListOverflow = 0xFFFFFFFFu;  // nbr_words value: list did not fit
 
-// self_seq[t] = position (word * 32 + bit) at which target lane t's own particle appears in
-// the warp's candidate sequence, recorded when it is staged (density.comp:110: the particle
-// itself is not a neighbour, so its bit is cleared from the masks).
-struct DensityStage {
-    float4 a[kStageCap];
+// ---------------------------------------------------------------------------------------
+// Group table.  One thread block walks the (y,z) rows of the offsets table in row order and
+// cuts each row's particle range into groups of <= 32: group_start[g] is the index of the
+// group's first particle in the sorted arrays, group_row[g] its row (z * G + y of the
+// table), *num_groups the total.  Rows [row_begin, row_end) are covered (slab mode skips the
+// two ghost layers).  Launch: <<<1, 1024>>>.
+__global__ void __launch_bounds__(1024)
+k_build_groups(const uint32_t* __restrict__ offsets, int G, int row_begin, int row_end,
+               uint32_t* __restrict__ group_start, uint32_t* __restrict__ group_row,
+               uint32_t* __restrict__ num_groups) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int r0 = row_begin; r0 < row_end; r0 += 1024) {
+        const int r = r0 + tid;
+        uint32_t beg = 0, ng = 0;
+        if (r < row_end) {
+            beg = offsets[(size_t)r * G];
+            ng = (offsets[(size_t)(r + 1) * G] - beg + 31u) >> 5;
+        }
+        uint32_t incl = ng;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = s_warp[lane];
+            uint32_t winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            s_warp[lane] = winc - w;
+        }
+        __syncthreads();
+        const uint32_t g = s_base + s_warp[warp] + (incl - ng);
+        // the warp fills the groups of its 32 rows together (a row can hold many groups)
+        for (int src = 0; src < 32; src++) {
+            const uint32_t n_src = __shfl_sync(0xffffffffu, ng, src);
+            const uint32_t g_src = __shfl_sync(0xffffffffu, g, src);
+            const uint32_t b_src = __shfl_sync(0xffffffffu, beg, src);
+            for (uint32_t k = lane; k < n_src; k += 32) {
+                group_start[g_src + k] = b_src + 32u * k;
+                group_row[g_src + k] = (uint32_t)(r0 + warp * 32 + src);
+            }
+        }
+        __syncthreads();
+        if (tid == 1023) s_base = g + ng;
+        __syncthreads();
+    }
+    if (tid == 0) *num_groups = s_base;
+}
+
+// Upper bound of the number of groups for n particles in `rows` rows.
+inline int max_groups(int n, long long rows) {
+    const long long nonempty = rows < n ? rows : n;
+    return (int)((n + 31) / 32 + nonempty);
+}
+
+// ---------------------------------------------------------------------------------------
+// Packed fp32 pairs (sm_100: add/sub/mul/fma .f32x2, round-to-nearest per half).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// Order-preserving float -> uint map, so warp min / max are single REDUX instructions.
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+    return __uint_as_float(u ^ (((int32_t)u >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+__device__ __forceinline__ float warp_min_f(float v, bool use) {
+    return ord2f(__reduce_min_sync(0xffffffffu, use ? f2ord(v) : 0xFFFFFFFFu));
+}
+__device__ __forceinline__ float warp_max_f(float v, bool use) {
+    return ord2f(__reduce_max_sync(0xffffffffu, use ? f2ord(v) : 0u));
+}
+
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---------------------------------------------------------------------------------------
+// Stages.  self_seq[t] = position (word * 32 + bit) at which target lane t's own particle
+// appears in the warp's candidate sequence, recorded when it is staged (density.comp:110:
+// the particle itself is not a neighbour, so its bit is cleared from the masks).
+struct alignas(16) DensityStage {
+    float x[kStageCap];
+    float y[kStageCap];
+    float z[kStageCap];
     uint32_t j[kStageCap];
     uint32_t self_seq[32];
-};
-struct UpdateStage {
-    float4 a[kStageCap];
-    float4 b[kStageCap];
-    uint32_t j[kStageCap];
-    uint32_t self_seq[32];
+    __device__ __forceinline__ void put(int slot, float4 q, uint32_t j_, const float4*) {
+        x[slot] = q.x, y[slot] = q.y, z[slot] = q.z, j[slot] = j_;
+    }
+    __device__ __forceinline__ void pad(int slot) {
+        x[slot] = kFar, y[slot] = kFar, z[slot] = kFar, j[slot] = kNoIndex;
+    }
+    __device__ __forceinline__ void move(int dst, int src, bool mv) {
+        float tx = 0, ty = 0, tz = 0;
+        uint32_t tj = 0;
+        if (mv) tx = x[src], ty = y[src], tz = z[src], tj = j[src];
+        __syncwarp();
+        if (mv) x[dst] = tx, y[dst] = ty, z[dst] = tz, j[dst] = tj;
+    }
 };
 
-// Neighbour list handed from the density pass to the update pass.  For every 32-target
-// warp the density kernel records, word by word, which 32 staged candidates it looked at
-// (nbr_idx) and which of them each lane accepted (nbr_mask, one bit per candidate).  The
-// update kernel replays the words: no second cull, no second distance test.  Layout:
-// [(warp * cap_words + word) * 32 + lane], i.e. one coalesced 128-byte line per word.
+// Update pass: a = (x, y, z, 1/rho), b = (vx, vy, vz, P); mask[w * 32 + lane] = the bits of
+// word w accepted by `lane`.  Sized for a replay batch; the no-list path uses the first
+// kStageCap slots in batches of kChunk.
+struct alignas(16) UpdateStage {
+    float4 a[kReplaySlots];
+    float4 b[kReplaySlots];
+    uint32_t mask[kReplayWords * 32];
+    uint32_t self_seq[32];
+    __device__ __forceinline__ void put(int slot, float4 q, uint32_t j_, const float4* vel_pres) {
+        q.w = __frcp_rn(q.w);  // the pair force only needs 1/rho_j
+        a[slot] = q;
+        b[slot] = vel_pres[j_];
+    }
+    __device__ __forceinline__ void pad(int slot) { a[slot] = make_float4(kFar, kFar, kFar, 0.0f); }
+    __device__ __forceinline__ void move(int dst, int src, bool mv) {
+        float4 ta, tb;
+        if (mv) ta = a[src], tb = b[src];
+        __syncwarp();
+        if (mv) a[dst] = ta, b[dst] = tb;
+    }
+};
+static_assert(kStageCap <= kReplaySlots, "the no-list path stages into the replay buffers");
+
+// Neighbour list handed from the density pass to the update pass.  Layout:
+// [(group * cap_words + word) * 32 + lane], i.e. one coalesced 128-byte line per word, for
+// both the candidate indices (idx) and the per-lane accept masks (mask).
 struct NbrList {
     uint32_t* idx;
     uint32_t* mask;
-    uint32_t* words;  // per warp: number of words, or kListOverflow
+    uint32_t* words;  // per group: number of words, or kListOverflow
     int cap_words;
 };
 
-// Per-lane accumulators and the batch processors -----------------------------------------
+// ---------------------------------------------------------------------------------------
+// Density accumulator: phase 2 of the file comment.
 template <bool kDebug>
 struct DensityAcc {
-    float sum = 0.0f;
+    float sum0 = 0.0f, sum1 = 0.0f;
     uint32_t nn = 0;
     uint32_t words_used = 0;
     bool overflow = false;
-    uint32_t* idx_out = nullptr;   // already offset to this warp's first word + lane
+    uint32_t* idx_out = nullptr;   // already offset to this group's first word + lane
     uint32_t* mask_out = nullptr;
     int cap_words = 0;
+
     // Runs this lane's target over stage[0, count); count is a multiple of 32.
     __device__ __forceinline__ void process(const DensityStage& st, int count, const SphConsts& c,
-                                            float4 p, float4, float Teff, uint32_t) {
+                                            float4 p, float4, float Teff) {
         const int lane = threadIdx.x & 31;
         const uint32_t self_seq = st.self_seq[lane];
+        const f32x2 PX = pack2(p.x, p.x), PY = pack2(p.y, p.y), PZ = pack2(p.z, p.z);
+        const f32x2 H2 = pack2(c.h2, c.h2);
         for (int k0 = 0; k0 < count; k0 += 32) {
             unsigned mk = 0u;
 #pragma unroll
-            for (int k = 0; k < 32; k++) {
-                const float4 q = st.a[k0 + k];
-                const float d2 = dist2(p.x - q.x, p.y - q.y, p.z - q.z);
-                if (d2 < Teff) {  // density.comp:117; the self pair (d2 = 0) is the m*poly6(0) term
-                    sum += poly6_t3(c.h2, d2);
-                    mk |= 1u << k;
+            for (int q = 0; q < 8; q++) {
+                const float4 X = *reinterpret_cast<const float4*>(&st.x[k0 + 4 * q]);
+                const float4 Y = *reinterpret_cast<const float4*>(&st.y[k0 + 4 * q]);
+                const float4 Z = *reinterpret_cast<const float4*>(&st.z[k0 + 4 * q]);
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const f32x2 rx = sub2(PX, hh ? pack2(X.z, X.w) : pack2(X.x, X.y));
+                    const f32x2 ry = sub2(PY, hh ? pack2(Y.z, Y.w) : pack2(Y.x, Y.y));
+                    const f32x2 rz = sub2(PZ, hh ? pack2(Z.z, Z.w) : pack2(Z.x, Z.y));
+                    // fma(rz,rz, fma(ry,ry, rx*rx)) per half: the oracle's pinned op order
+                    const f32x2 d2 = fma2(rz, rz, fma2(ry, ry, mul2(rx, rx)));
+                    const f32x2 t = sub2(H2, d2);       // density.comp:54, on squared distances
+                    const f32x2 tt = mul2(t, t);
+                    float d2a, d2b, ta, tb, tta, ttb;
+                    unpack2(d2, d2a, d2b);
+                    unpack2(t, ta, tb);
+                    unpack2(tt, tta, ttb);
+                    // density.comp:117; the self pair (d2 = 0) is the m * poly6(0) term
+                    if (d2a < Teff) {
+                        sum0 = fmaf(tta, ta, sum0);
+                        mk |= 1u << (4 * q + 2 * hh);
+                    }
+                    if (d2b < Teff) {
+                        sum1 = fmaf(ttb, tb, sum1);
+                        mk |= 1u << (4 * q + 2 * hh + 1);
+                    }
                 }
             }
             if (words_used == (self_seq >> 5)) mk &= ~(1u << (self_seq & 31u));  // density.comp:110
@@ -110,17 +277,11 @@ struct DensityAcc {
     }
 };
 
-__device__ __forceinline__ float rsqrt_approx(float x) {
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// Stage layout of the update pass: a = (x, y, z, 1/rho), b = (vx, vy, vz, P).
+// Update accumulator.
 struct UpdateAcc {
     // Fp is accumulated without its factor -0.5 * m * spikyC, Fv without m * viscC.
     float Fpx = 0, Fpy = 0, Fpz = 0, Fvx = 0, Fvy = 0, Fvz = 0;
-    uint32_t words_used = 0;  // words of the candidate sequence processed so far (full path)
+    uint32_t words_used = 0;  // words of the candidate sequence processed so far (no-list path)
 
     // One accepted pair of update.comp:174-187.
     __device__ __forceinline__ void pair(const SphConsts& c, float4 p, float4 v, float4 qa,
@@ -137,248 +298,259 @@ struct UpdateAcc {
         Fvz = fmaf(wv, qb.z - v.z, Fvz);
     }
 
-    // phase 2: every lane walks its own accepted candidates.  The four mask words of a batch
-    // sit in a per-lane shift register (m0 is the word being drained, base its first slot),
-    // so a lane moves on to its next word while others are still busy with theirs.
-    __device__ __forceinline__ void pairs(const UpdateStage& st, unsigned m0, unsigned m1,
-                                          unsigned m2, unsigned m3, const SphConsts& c, float4 p,
-                                          float4 v) {
-        int base = 0;
-        while (__any_sync(0xffffffffu, (m0 | m1 | m2 | m3) != 0u)) {
-            if (m0 == 0u) {
-                m0 = m1, m1 = m2, m2 = m3, m3 = 0u;
-                base += 32;
-            }
-            if (m0 != 0u) {
-                const int slot = base + __ffs((int)m0) - 1;
-                m0 &= m0 - 1u;
+    // Every lane walks its own accepted bits of st.mask[0, nw) -- one flat loop over the
+    // whole batch, so lanes only wait for each other at the batch's end.
+    __device__ __forceinline__ void walk(const UpdateStage& st, int nw, const SphConsts& c,
+                                         float4 p, float4 v) {
+        const int lane = threadIdx.x & 31;
+        int n = 0;
+#pragma unroll
+        for (int w = 0; w < kReplayWords; w++)
+            if (w < nw) n += __popc(st.mask[w * 32 + lane]);
+        const int nmax = __reduce_max_sync(0xffffffffu, n);
+        int w = -1;
+        unsigned m = 0u;
+        for (int it = 0; it < nmax; it++) {
+            if (it < n) {
+                while (m == 0u) m = st.mask[++w * 32 + lane];  // it < n: a set bit remains
+                const int pos = 31 - __clz((int)m);
+                m ^= 1u << pos;
+                const int slot = w * 32 + pos;
                 pair(c, p, v, st.a[slot], st.b[slot]);
             }
         }
     }
 
-    // Full path (no list): phase 1 = distance test only -> one bit per staged candidate.
-    __device__ __forceinline__ void process(const UpdateStage& st, int count, const SphConsts& c,
-                                            float4 p, float4 v, float Teff, uint32_t) {
-        const uint32_t self_seq = st.self_seq[threadIdx.x & 31];
-        unsigned mk[kChunk / 32];
-#pragma unroll
-        for (int w = 0; w < kChunk / 32; w++) {
-            mk[w] = 0u;
-            if (w * 32 < count) {
-#pragma unroll
-                for (int k = 0; k < 32; k++) {
-                    const float4 q = st.a[w * 32 + k];
-                    const float d2 = dist2(p.x - q.x, p.y - q.y, p.z - q.z);
-                    mk[w] |= (d2 < Teff) ? (1u << k) : 0u;
-                }
-                if (words_used == (self_seq >> 5)) mk[w] &= ~(1u << (self_seq & 31u));
-                words_used++;
+    // No-list path: phase 1 = distance test only -> one bit per staged candidate, then walk.
+    __device__ __forceinline__ void process(UpdateStage& st, int count, const SphConsts& c,
+                                            float4 p, float4 v, float Teff) {
+        const int lane = threadIdx.x & 31;
+        const uint32_t self_seq = st.self_seq[lane];
+        const int nw = count >> 5;
+        for (int w = 0; w < nw; w++) {
+            unsigned mk = 0u;
+#pragma unroll 8
+            for (int k = 0; k < 32; k++) {
+                const float4 q = st.a[w * 32 + k];
+                const float d2 = dist2(p.x - q.x, p.y - q.y, p.z - q.z);
+                mk |= (d2 < Teff) ? (1u << k) : 0u;
             }
+            if (words_used == (self_seq >> 5)) mk &= ~(1u << (self_seq & 31u));
+            words_used++;
+            st.mask[w * 32 + lane] = mk;
         }
-        pairs(st, mk[0], mk[1], mk[2], mk[3], c, p, v);
+        __syncwarp();
+        walk(st, nw, c, p, v);
     }
 };
-static_assert(kChunk == 128, "UpdateAcc::pairs drains four 32-bit mask words per batch");
 
-// The shared gather driver ----------------------------------------------------------------
-// kUpdate selects what is staged (positions only, or positions + velocities + index).
-template <bool kUpdate, typename Stage, typename Acc>
-__device__ __forceinline__ void gather_rows(const float4* pos_rho, const float4* vel_pres,
-                                            const uint32_t* __restrict__ offsets,
-                                            const SphConsts& c, Stage& st, Acc& acc, bool valid,
-                                            uint32_t self, float4 p, float4 v) {
+// ---------------------------------------------------------------------------------------
+// The shared gather driver: phase 1 (cull + stage) and the hand-over to acc.process().
+struct GroupGeom {
+    int x0, x1;        // cell columns of the nine slices
+    int ry, rz;        // the group's cell row (rz relative to the table's layer 0)
+};
+
+template <typename Stage, typename Acc>
+__device__ __forceinline__ void gather_group(const float4* pos_rho, const float4* vel_pres,
+                                             const uint32_t* __restrict__ offsets,
+                                             const SphConsts& c, Stage& st, Acc& acc, bool valid,
+                                             uint32_t wfirst, const GroupGeom& gg, float4 p,
+                                             float4 v) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int G = c.G;
-    int cx = 0, cy = 0, cz = 0, row = -1;
-    if (valid) {
-        cx = cell_coord(p.x, c.bin, G), cy = cell_coord(p.y, c.bin, G),
-        cz = cell_coord(p.z, c.bin, G) - c.zbase;
-        row = cz * G + cy;
-    }
+    // NaN targets never accept anything; keep them out of the box so it stays finite.
+    const bool box = valid && p.x == p.x && p.y == p.y && p.z == p.z;
+    const float bx0 = warp_min_f(p.x, box), bx1 = warp_max_f(p.x, box);
+    const float by0 = warp_min_f(p.y, box), by1 = warp_max_f(p.y, box);
+    const float bz0 = warp_min_f(p.z, box), bz1 = warp_max_f(p.z, box);
     const float Tcull = c.T * 1.0001f;  // conservative: rounding in the box distance
-    const uint32_t wfirst = self - (uint32_t)lane;  // index of the warp's first target
+    const float Teff = valid ? c.T : -1.0f;
     st.self_seq[lane] = kNoIndex;
     __syncwarp();
 
-    unsigned rem = __ballot_sync(full, valid);
-    while (rem) {
-        // ---- the lanes of one (y,z) cell row are consecutive (array is cell-sorted)
-        const int leader = __ffs(rem) - 1;
-        const int r = __shfl_sync(full, row, leader);
-        const bool inrow = valid && row == r;
-        const unsigned m = __ballot_sync(full, inrow);
-        rem &= ~m;
-        const int xlo = __shfl_sync(full, cx, __ffs(m) - 1);
-        const int xhi = __shfl_sync(full, cx, 31 - __clz(m));
-        const int x0 = max(xlo - 1, 0), x1 = min(xhi + 1, G - 1);
-        const int ry = __shfl_sync(full, cy, leader), rz = __shfl_sync(full, cz, leader);
-        const float bx0 = warp_min_f(inrow ? p.x : INFINITY), bx1 = warp_max_f(inrow ? p.x : -INFINITY);
-        const float by0 = warp_min_f(inrow ? p.y : INFINITY), by1 = warp_max_f(inrow ? p.y : -INFINITY);
-        const float bz0 = warp_min_f(inrow ? p.z : INFINITY), bz1 = warp_max_f(inrow ? p.z : -INFINITY);
-        const float Teff = inrow ? c.T : -1.0f;  // lanes of other rows never accept
-
-        // ---- the nine slices (density.comp:95-101: rows outside the grid are skipped)
-        uint32_t sbeg = 0, send = 0;
-        if (lane < 9) {
-            const int z = rz + lane / 3 - 1, y = ry + lane % 3 - 1;
-            if (z >= 0 && z < c.Gz && y >= 0 && y < G) {
-                const uint32_t rowbase = ((uint32_t)z * G + (uint32_t)y) * G;
-                sbeg = offsets[rowbase + x0];
-                send = offsets[rowbase + x1 + 1];
+    // the nine slices (density.comp:95-101: rows outside the grid are skipped)
+    uint32_t sbeg = 0, send = 0;
+    if (lane < 9) {
+        const int z = gg.rz + lane / 3 - 1, y = gg.ry + lane % 3 - 1;
+        if (z >= 0 && z < c.Gz && y >= 0 && y < G) {
+            const uint32_t rowbase = ((uint32_t)z * G + (uint32_t)y) * G;
+            sbeg = offsets[rowbase + gg.x0];
+            send = offsets[rowbase + gg.x1 + 1];
+        }
+    }
+    int s = 0, cnt = 0;
+    uint32_t j0 = __shfl_sync(full, sbeg, 0), end = __shfl_sync(full, send, 0);
+    bool done = false;
+    while (true) {
+        while (!done && j0 >= end) {
+            if (++s == 9) {
+                done = true;
+            } else {
+                j0 = __shfl_sync(full, sbeg, s);
+                end = __shfl_sync(full, send, s);
             }
         }
-        int s = 0, cnt = 0;
-        uint32_t j0 = __shfl_sync(full, sbeg, 0), end = __shfl_sync(full, send, 0);
-        bool done = false;
-        while (true) {
-            while (!done && j0 >= end) {
-                if (++s == 9) {
-                    done = true;
-                } else {
-                    j0 = __shfl_sync(full, sbeg, s);
-                    end = __shfl_sync(full, send, s);
-                }
+        if (!done) {
+            // cull 32 candidates against the targets' box grown by h
+            const uint32_t j = j0 + lane;
+            const bool ok = j < end;
+            float4 q = make_float4(kFar, kFar, kFar, 0.0f);
+            if (ok) q = pos_rho[j];
+            const float ex = fmaxf(fmaxf(bx0 - q.x, q.x - bx1), 0.0f);
+            const float ey = fmaxf(fmaxf(by0 - q.y, q.y - by1), 0.0f);
+            const float ez = fmaxf(fmaxf(bz0 - q.z, q.z - bz1), 0.0f);
+            const bool keep = ok && (ex * ex + ey * ey + ez * ez < Tcull);
+            const unsigned km = __ballot_sync(full, keep);
+            if (keep) {
+                const int slot = cnt + __popc(km & lt);
+                st.put(slot, q, j, vel_pres);
+                if (j - wfirst < 32u) st.self_seq[j - wfirst] = acc.words_used * 32u + (uint32_t)slot;
             }
-            if (!done) {
-                // ---- cull 32 candidates against the targets' box grown by h
-                const uint32_t j = j0 + lane;
-                const bool ok = j < end;
-                float4 q = make_float4(kFar, kFar, kFar, 0.0f);
-                if (ok) q = pos_rho[j];
-                const float ex = fmaxf(fmaxf(bx0 - q.x, q.x - bx1), 0.0f);
-                const float ey = fmaxf(fmaxf(by0 - q.y, q.y - by1), 0.0f);
-                const float ez = fmaxf(fmaxf(bz0 - q.z, q.z - bz1), 0.0f);
-                const bool keep = ok && (ex * ex + ey * ey + ez * ez < Tcull);
-                const unsigned km = __ballot_sync(full, keep);
-                if (keep) {
-                    const int slot = cnt + __popc(km & lt);
-                    if constexpr (kUpdate) {
-                        q.w = __frcp_rn(q.w);  // the pair force only needs 1/rho_j
-                        st.b[slot] = vel_pres[j];
-                    }
-                    st.a[slot] = q;
-                    st.j[slot] = j;
-                    if (j - wfirst < 32u) st.self_seq[j - wfirst] = acc.words_used * 32u + (uint32_t)slot;
-                }
-                cnt += __popc(km);
-                j0 += 32;
-            }
-            if (cnt >= kChunk || (done && cnt > 0)) {
-                int count = kChunk;
-                if (cnt < kChunk) {  // final partial batch: pad to a multiple of 32
-                    count = (cnt + 31) & ~31;
-                    if (cnt + lane < count) {
-                        st.a[cnt + lane] = make_float4(kFar, kFar, kFar, 0.0f);
-                        st.j[cnt + lane] = kNoIndex;
-                    }
-                }
-                __syncwarp();
-                acc.process(st, count, c, p, v, Teff, self);
-                __syncwarp();
-                // move the (< 32) leftovers to the front
-                const int left = cnt - min(cnt, kChunk);
-                if (left > 0) {
-                    float4 ta, tb;
-                    uint32_t tj = 0;
-                    const bool mv = lane < left;
-                    if (mv) {
-                        ta = st.a[kChunk + lane];
-                        tj = st.j[kChunk + lane];
-                        if constexpr (kUpdate) tb = st.b[kChunk + lane];
-                    }
-                    __syncwarp();
-                    if (mv) {
-                        st.a[lane] = ta;
-                        st.j[lane] = tj;
-                        if constexpr (kUpdate) st.b[lane] = tb;
-                    }
-                    __syncwarp();
-                }
-                cnt = left;
-            }
-            if (done && cnt == 0) break;
+            cnt += __popc(km);
+            j0 += 32;
         }
+        if (cnt >= kChunk || (done && cnt > 0)) {
+            int count = kChunk;
+            if (cnt < kChunk) {  // final partial batch: pad to a multiple of 32
+                count = (cnt + 31) & ~31;
+                if (cnt + lane < count) st.pad(cnt + lane);
+            }
+            __syncwarp();
+            acc.process(st, count, c, p, v, Teff);
+            __syncwarp();
+            const int left = cnt - min(cnt, kChunk);  // move the (< 32) leftovers to the front
+            if (left > 0) {
+                st.move(lane, kChunk + lane, lane < left);
+                __syncwarp();
+            }
+            cnt = left;
+        }
+        if (done && cnt == 0) break;
     }
 }
 
+// Common prologue: which group this warp owns, its targets and row geometry.
+struct GroupCtx {
+    int g;           // group number
+    int t;           // this lane's target number within the launch (output index)
+    int i;           // this lane's particle index in the candidate arrays
+    bool active;     // the warp has a group
+    bool valid;      // this lane has a target
+    uint32_t wfirst;
+    GroupGeom gg;
+};
+
+__device__ __forceinline__ GroupCtx group_prologue(const float4* pos_rho,
+                                                   const uint32_t* __restrict__ offsets,
+                                                   const SphConsts& c,
+                                                   const uint32_t* __restrict__ group_start,
+                                                   const uint32_t* __restrict__ group_row,
+                                                   const uint32_t* __restrict__ num_groups,
+                                                   int warps_per_block, float4* p_out) {
+    GroupCtx x;
+    const int lane = threadIdx.x & 31;
+    x.g = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    x.active = (uint32_t)x.g < *num_groups;
+    x.valid = false;
+    x.t = x.i = 0;
+    x.wfirst = 0;
+    *p_out = make_float4(0, 0, 0, 0);
+    if (!x.active) return x;
+    const uint32_t i0 = group_start[x.g];
+    x.wfirst = i0;
+    const uint32_t row = group_row[x.g];  // every group has at least one particle
+    const int G = c.G;
+    x.gg.rz = (int)(row / (uint32_t)G);
+    x.gg.ry = (int)(row - (uint32_t)x.gg.rz * (uint32_t)G);
+    const uint32_t row_end = offsets[((size_t)row + 1) * G];
+    const int cnt = (int)min(32u, row_end - i0);
+    x.valid = lane < cnt;
+    x.i = (int)i0 + lane;
+    x.t = x.i - c.first;
+    float4 p = make_float4(0, 0, 0, 0);
+    if (x.valid) p = pos_rho[x.i];
+    *p_out = p;
+    // cells ascend along the row, so the first / last valid lanes bound the x range
+    const int cx = x.valid ? cell_coord(p.x, c.bin, G) : 0;
+    const int xlo = __shfl_sync(0xffffffffu, cx, 0), xhi = __shfl_sync(0xffffffffu, cx, cnt - 1);
+    x.gg.x0 = max(xlo - 1, 0);
+    x.gg.x1 = min(xhi + 1, G - 1);
+    return x;
+}
+
 template <bool kDebug>
-__global__ void __launch_bounds__(kTileWarps * 32)
+__global__ void __launch_bounds__(kDensityWarps * 32)
 k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
                const uint32_t* __restrict__ offsets, SphConsts c,
-               uint32_t* __restrict__ neighbour_counts, NbrList list) {
-    __shared__ DensityStage s_stage[kTileWarps];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wg = blockIdx.x * kTileWarps + warp;
-    const int t = wg * 32 + lane;         // target number within this launch
-    const int i = c.first + t;            // its index in the candidate arrays
-    const bool valid = t < c.n;
-    float4 p = make_float4(0, 0, 0, 0);
-    if (valid) p = pos_rho[i];
+               const uint32_t* __restrict__ group_start, const uint32_t* __restrict__ group_row,
+               const uint32_t* __restrict__ num_groups, uint32_t* __restrict__ neighbour_counts,
+               NbrList list) {
+    __shared__ DensityStage s_stage[kDensityWarps];
+    const int lane = threadIdx.x & 31;
+    float4 p;
+    const GroupCtx x = group_prologue(pos_rho, offsets, c, group_start, group_row, num_groups,
+                                      kDensityWarps, &p);
+    if (!x.active) return;
     DensityAcc<kDebug> acc;
     if (list.idx) {
-        acc.idx_out = list.idx + (size_t)wg * list.cap_words * 32 + lane;
-        acc.mask_out = list.mask + (size_t)wg * list.cap_words * 32 + lane;
+        acc.idx_out = list.idx + (size_t)x.g * list.cap_words * 32 + lane;
+        acc.mask_out = list.mask + (size_t)x.g * list.cap_words * 32 + lane;
         acc.cap_words = list.cap_words;
     }
-    gather_rows<false>(pos_rho, vel_pres, offsets, c, s_stage[warp], acc, valid, (uint32_t)i, p,
-                       make_float4(0, 0, 0, 0));
-    if (list.idx && lane == 0 && wg * 32 < c.n)
-        list.words[wg] = acc.overflow ? kListOverflow : acc.words_used;
-    if (!valid) return;
+    gather_group(pos_rho, vel_pres, offsets, c, s_stage[threadIdx.x >> 5], acc, x.valid, x.wfirst,
+                 x.gg, p, make_float4(0, 0, 0, 0));
+    if (list.idx && lane == 0) list.words[x.g] = acc.overflow ? kListOverflow : acc.words_used;
+    if (!x.valid) return;
     float rho, pres;
-    finish_density(c, acc.sum, p.x, p.y, p.z, &rho, &pres);
+    finish_density(c, acc.sum0 + acc.sum1, p.x, p.y, p.z, &rho, &pres);
     // In place like density.comp:135; the gather only reads x,y,z, which do not change.
-    reinterpret_cast<float*>(pos_rho)[4 * (size_t)i + 3] = rho;
-    reinterpret_cast<float*>(vel_pres)[4 * (size_t)i + 3] = pres;
-    if (kDebug) neighbour_counts[t] = acc.nn;  // the self pair's bit is already cleared
+    reinterpret_cast<float*>(pos_rho)[4 * (size_t)x.i + 3] = rho;
+    reinterpret_cast<float*>(vel_pres)[4 * (size_t)x.i + 3] = pres;
+    if (kDebug) neighbour_counts[x.t] = acc.nn;  // the self pair's bit is already cleared
 }
 
 // update.comp:134-232.  With a valid neighbour list the warp replays the density pass's
-// words (gather by index into the stage, then pairs()); without one (list.idx == nullptr,
-// or this warp overflowed its list) it runs the full cull + distance test itself.
+// words; without one (list.idx == nullptr, or this group overflowed its list) it runs the
+// cull + distance test itself.
 template <bool kDebug>
-__global__ void __launch_bounds__(kTileWarps * 32)
+__global__ void __launch_bounds__(kUpdateWarps * 32)
 k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel_pres,
-              const uint32_t* __restrict__ offsets, SphConsts c, float4* __restrict__ pos_out,
-              float4* __restrict__ vel_out, float4* __restrict__ forces, NbrList list) {
-    __shared__ UpdateStage s_stage[kTileWarps];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wg = blockIdx.x * kTileWarps + warp;
-    const int t = wg * 32 + lane;
-    const int i = c.first + t;
-    const bool valid = t < c.n;
-    float4 p = make_float4(0, 0, 0, 0), v = make_float4(0, 0, 0, 0);
-    if (valid) {
-        p = pos_rho[i];
-        v = vel_pres[i];
-    }
+              const uint32_t* __restrict__ offsets, SphConsts c,
+              const uint32_t* __restrict__ group_start, const uint32_t* __restrict__ group_row,
+              const uint32_t* __restrict__ num_groups, float4* __restrict__ pos_out, float4* __restrict__ vel_out,
+              float4* __restrict__ forces, NbrList list) {
+    __shared__ UpdateStage s_stage[kUpdateWarps];
+    const int lane = threadIdx.x & 31;
+    float4 p;
+    const GroupCtx x = group_prologue(pos_rho, offsets, c, group_start, group_row, num_groups,
+                                      kUpdateWarps, &p);
+    if (!x.active) return;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (x.valid) v = vel_pres[x.i];
     UpdateAcc acc;
-    UpdateStage& st = s_stage[warp];
+    UpdateStage& st = s_stage[threadIdx.x >> 5];
     uint32_t nw = kListOverflow;
-    if (list.idx && wg * 32 < c.n) nw = list.words[wg];
+    if (list.idx) nw = list.words[x.g];
     if (nw == kListOverflow) {
-        if (wg * 32 < c.n)
-            gather_rows<true>(pos_rho, vel_pres, offsets, c, st, acc, valid, (uint32_t)i, p, v);
+        gather_group(pos_rho, vel_pres, offsets, c, st, acc, x.valid, x.wfirst, x.gg, p, v);
     } else {
-        const uint32_t* widx = list.idx + (size_t)wg * list.cap_words * 32 + lane;
-        const uint32_t* wmask = list.mask + (size_t)wg * list.cap_words * 32 + lane;
-        for (uint32_t w0 = 0; w0 < nw; w0 += kChunk / 32) {
-            unsigned mk[kChunk / 32];
-            uint32_t jj[kChunk / 32];
+        const uint32_t* widx = list.idx + (size_t)x.g * list.cap_words * 32 + lane;
+        const uint32_t* wmask = list.mask + (size_t)x.g * list.cap_words * 32 + lane;
+        for (uint32_t w0 = 0; w0 < nw; w0 += kReplayWords) {
+            uint32_t jj[kReplayWords];
 #pragma unroll
-            for (int u = 0; u < kChunk / 32; u++) {
-                mk[u] = 0u;
+            for (int u = 0; u < kReplayWords; u++) {
                 jj[u] = kNoIndex;
                 if (w0 + u < nw) {
                     jj[u] = widx[(size_t)(w0 + u) * 32];
-                    mk[u] = wmask[(size_t)(w0 + u) * 32];
+                    st.mask[u * 32 + lane] = wmask[(size_t)(w0 + u) * 32];
                 }
             }
 #pragma unroll
-            for (int u = 0; u < kChunk / 32; u++) {
+            for (int u = 0; u < kReplayWords; u++) {
                 if (jj[u] != kNoIndex) {
                     float4 qa = pos_rho[jj[u]];
                     qa.w = __frcp_rn(qa.w);
@@ -387,47 +559,54 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
                 }
             }
             __syncwarp();
-            acc.pairs(st, mk[0], mk[1], mk[2], mk[3], c, p, v);
+            acc.walk(st, (int)min((uint32_t)kReplayWords, nw - w0), c, p, v);
             __syncwarp();
         }
     }
-    if (!valid) return;
+    if (!x.valid) return;
     const float kp = -0.5f * (c.m * c.spikyC), kv = c.m * c.viscC;
     float4 po, vo, fo;
     integrate(c, p, v, acc.Fpx * kp, acc.Fpy * kp, acc.Fpz * kp, acc.Fvx * kv, acc.Fvy * kv,
               acc.Fvz * kv, &po, &vo, kDebug ? &fo : nullptr);
-    pos_out[t] = po;
-    vel_out[t] = vo;
-    if (kDebug) forces[t] = fo;
+    pos_out[x.t] = po;
+    vel_out[x.t] = vo;
+    if (kDebug) forces[x.t] = fo;
 }
 
-inline int tile_blocks(int n) { return (n + kTileWarps * 32 - 1) / (kTileWarps * 32); }
-inline int tile_warps(int n) { return tile_blocks(n) * kTileWarps; }
+struct GroupTable {
+    const uint32_t* start;
+    const uint32_t* row;
+    const uint32_t* count;  // device scalar
+    int max_groups;         // launch bound (>= *count)
+};
 
-// Returns 0 when launched, -1 when the geometry is not covered (never, currently).
-inline int launch_density_tile(float4* pos_rho, float4* vel_pres, const uint32_t* offsets,
-                               const SphConsts& c, uint32_t* neighbour_counts, NbrList list,
-                               cudaStream_t stream) {
+inline int blocks_for(int groups, int warps) { return (groups + warps - 1) / warps; }
+
+inline void launch_density_tile(float4* pos_rho, float4* vel_pres, const uint32_t* offsets,
+                                const SphConsts& c, const GroupTable& gt,
+                                uint32_t* neighbour_counts, NbrList list, cudaStream_t stream) {
+    const int blocks = blocks_for(gt.max_groups, kDensityWarps);
     if (neighbour_counts)
-        k_density_tile<true><<<tile_blocks(c.n), kTileWarps * 32, 0, stream>>>(
-            pos_rho, vel_pres, offsets, c, neighbour_counts, list);
+        k_density_tile<true><<<blocks, kDensityWarps * 32, 0, stream>>>(
+            pos_rho, vel_pres, offsets, c, gt.start, gt.row, gt.count, neighbour_counts, list);
     else
-        k_density_tile<false><<<tile_blocks(c.n), kTileWarps * 32, 0, stream>>>(
-            pos_rho, vel_pres, offsets, c, nullptr, list);
-    return 0;
+        k_density_tile<false><<<blocks, kDensityWarps * 32, 0, stream>>>(
+            pos_rho, vel_pres, offsets, c, gt.start, gt.row, gt.count, nullptr, list);
 }
 
-inline int launch_update_tile(const float4* pos_rho, const float4* vel_pres,
-                              const uint32_t* offsets, const SphConsts& c, float4* pos_out,
-                              float4* vel_out, float4* forces, NbrList list,
-                              cudaStream_t stream) {
+inline void launch_update_tile(const float4* pos_rho, const float4* vel_pres,
+                               const uint32_t* offsets, const SphConsts& c, const GroupTable& gt,
+                               float4* pos_out, float4* vel_out, float4* forces, NbrList list,
+                               cudaStream_t stream) {
+    const int blocks = blocks_for(gt.max_groups, kUpdateWarps);
     if (forces)
-        k_update_tile<true><<<tile_blocks(c.n), kTileWarps * 32, 0, stream>>>(
-            pos_rho, vel_pres, offsets, c, pos_out, vel_out, forces, list);
+        k_update_tile<true><<<blocks, kUpdateWarps * 32, 0, stream>>>(
+            pos_rho, vel_pres, offsets, c, gt.start, gt.row, gt.count, pos_out, vel_out, forces,
+            list);
     else
-        k_update_tile<false><<<tile_blocks(c.n), kTileWarps * 32, 0, stream>>>(
-            pos_rho, vel_pres, offsets, c, pos_out, vel_out, nullptr, list);
-    return 0;
+        k_update_tile<false><<<blocks, kUpdateWarps * 32, 0, stream>>>(
+            pos_rho, vel_pres, offsets, c, gt.start, gt.row, gt.count, pos_out, vel_out, nullptr,
+            list);
 }
 
 }  // namespace wc

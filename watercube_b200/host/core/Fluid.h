@@ -1,0 +1,100 @@
+// core/Fluid.h -- host facade of the SPH solver.
+//
+// Keeps the setup / update / particle-buffer surface of the reference's core::Fluid
+// (src/core/Fluid.h:32-59) so that Scene::update (Scene.cpp:52-56) -- and with it the Cinder
+// app's update call (WaterCubeApp.cpp:98) -- can drive the B200 path unchanged: same fluent
+// setters, same setup(), same virtual update(double time).  All device work goes through the
+// C-ABI of include/wc_sph.h; there is no CPU fallback (setup() throws core::Error when no
+// sm_100 device is usable).  Rendering and the AntTweakBar panel (Fluid.cpp:89-99,
+// :359-431) are out of scope: draw() is a no-op and the GUI-bound fields are plain members
+// read on every update, exactly as the reference re-uploads them as uniforms every frame
+// (Fluid.cpp:276-285, :305-317).
+#pragma once
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "./BaseObject.h"
+#include "./Sort.h"
+#include "./util.h"
+
+namespace core {
+
+typedef std::shared_ptr<class Fluid> FluidRef;
+
+class Fluid : public BaseObject, public std::enable_shared_from_this<Fluid> {
+public:
+    explicit Fluid(const std::string& name);
+    ~Fluid();
+    Fluid(const Fluid&) = delete;
+    Fluid& operator=(const Fluid&) = delete;
+
+    int numParticles() { return num_particles_; }
+    // Setup-time setters (call before setup(), Fluid.cpp:31-84).  They return the object
+    // itself rather than the reference's copies (quirk Q17).
+    FluidRef numParticles(int n);
+    FluidRef gridRes(int r);
+    FluidRef size(float s);
+    FluidRef particleRadius(float r);
+    FluidRef position(vec3 p);
+    FluidRef renderMode(int m);
+    FluidRef device(int ordinal);            // new: CUDA device ordinal
+    FluidRef seed(uint32_t s);               // new: seed of the portable jitter generator (Q16)
+    // Per-step mutable (GUI-bound in the reference).
+    FluidRef viscosityCoefficient(float c);
+    FluidRef stiffness(float s);
+    FluidRef restDensity(float d);
+    FluidRef restPressure(float p);
+    FluidRef gravityStrength(float g);
+    FluidRef gravityDirection(vec3 d);       // what "Rotate Gravity" updates (Fluid.cpp:259-263)
+
+    void setCameraPosition(vec3 p) { camera_position_ = p; }
+    void setLightPosition(vec3 p) { light_position_ = p; }
+    void setMouseRay(Ray r) { mouse_ray_ = r; has_mouse_ray_ = true; }
+
+    // Replace the generated lattice with caller-provided particles (before or after setup()).
+    FluidRef initialParticles(const std::vector<Particle>& particles);
+
+    FluidRef setup();                    // Fluid.cpp:203-235
+    void update(double time) override;   // Fluid.cpp:342-354
+    void draw() override {}              // graphics, out of scope
+    void reset() override;               // WaterCubeApp.cpp:81-88: rebuild from the initial state
+
+    // The particle-buffer surface: buffer 1 = current state (what the renderer binds,
+    // Fluid.cpp:394), buffer 2 = cell-sorted input of the last step with density / pressure.
+    Buffer particleBuffer1() const { return Buffer{handle_, BufferKind::Particles1}; }
+    Buffer particleBuffer2() const { return Buffer{handle_, BufferKind::Particles2}; }
+    SortRef sort() const { return sort_; }
+    wc_handle* nativeHandle() const { return handle_; }
+
+    // Derived constants of Fluid::setup (Fluid.cpp:206-216).
+    float binSize() const { return derived_.bin_size; }
+    float kernelRadius() const { return derived_.kernel_radius; }
+    float particleMass() const { return derived_.particle_mass; }
+    int numBins() const { return derived_.num_bins; }
+    const std::vector<Particle>& initialParticlesRef() const { return initial_particles_; }
+
+    static FluidRef create(const std::string& name) { return std::make_shared<Fluid>(name); }
+
+protected:
+    void generateInitialParticles();  // Fluid.cpp:104-134 with a portable generator (Q16)
+    Ray getRelativeMouseRay() const;  // Fluid.cpp:251-256
+    void runDensityProg(Buffer particle_buffer);                              // Fluid.cpp:268
+    void runUpdateProg(Buffer in_particles, Buffer out_particles, float time_step);  // :294
+    wc_step_params stepParams() const;
+
+    int num_particles_, grid_res_, render_mode_, device_;
+    uint32_t seed_;
+    float size_, particle_radius_, viscosity_coefficient_, stiffness_, rest_density_,
+        rest_pressure_, gravity_strength_, time_scale_;
+    vec3 position_, camera_position_, light_position_, gravity_direction_;
+    Ray mouse_ray_;
+    bool has_mouse_ray_, user_particles_;
+    std::vector<Particle> initial_particles_;
+    SortRef sort_;
+    wc_handle* handle_;
+    wc_derived derived_;
+};
+
+}  // namespace core

@@ -1,0 +1,84 @@
+// core/util.cpp -- see util.h.  Reference: src/core/util.cpp.
+#include "./util.h"
+
+#include <cstdarg>
+#include <cstdio>
+
+namespace core {
+namespace util {
+
+void check(int rc) {
+    if (rc != WC_OK) throw Error(rc, std::string("wc_sph: ") + wc_last_error());
+}
+
+void log(const char* format, ...) {
+    va_list args;
+    va_start(args, format);
+    std::vfprintf(stderr, format, args);
+    va_end(args);
+}
+
+static wc_handle* need(Buffer b, const char* who) {
+    if (!b) throw Error(WC_ERR_INVALID, std::string(who) + ": null buffer");
+    return b.handle;
+}
+
+std::vector<Particle> getParticles(Buffer buffer, int num_items) {
+    wc_handle* h = need(buffer, "getParticles");
+    if (buffer.kind != BufferKind::Particles1 && buffer.kind != BufferKind::Particles2)
+        throw Error(WC_ERR_INVALID, "getParticles: not a particle buffer");
+    wc_device_view view;
+    check(wc_device_ptrs(h, &view));
+    std::vector<Particle> all((size_t)view.num_particles);
+    check(wc_download_particles(h, (int)buffer.kind, reinterpret_cast<wc_particle*>(all.data())));
+    if (num_items >= 0 && (size_t)num_items < all.size()) all.resize((size_t)num_items);
+    return all;
+}
+
+void setParticles(Buffer buffer, const std::vector<Particle>& particles) {
+    wc_handle* h = need(buffer, "setParticles");
+    const wc_particle* src = reinterpret_cast<const wc_particle*>(particles.data());
+    if (buffer.kind == BufferKind::Particles1)
+        check(wc_upload_particles(h, src, (int32_t)particles.size()));
+    else if (buffer.kind == BufferKind::Particles2)
+        check(wc_upload_sorted(h, src, (int32_t)particles.size()));
+    else
+        throw Error(WC_ERR_INVALID, "setParticles: not a particle buffer");
+}
+
+std::vector<uint32_t> getUints(Buffer buffer, int num_items) {
+    wc_handle* h = need(buffer, "getUints");
+    wc_device_view view;
+    check(wc_device_ptrs(h, &view));
+    wc_derived d;
+    check(wc_get_derived(h, &d));
+    const bool per_bin = buffer.kind == BufferKind::Counts || buffer.kind == BufferKind::Offsets;
+    std::vector<uint32_t> out(per_bin ? (size_t)d.num_bins : (size_t)view.num_particles);
+    uint32_t* p = out.data();
+    switch (buffer.kind) {
+        case BufferKind::CellIds: check(wc_download_cells(h, p, nullptr, nullptr, nullptr, nullptr)); break;
+        case BufferKind::Counts: check(wc_download_cells(h, nullptr, p, nullptr, nullptr, nullptr)); break;
+        case BufferKind::Offsets: check(wc_download_cells(h, nullptr, nullptr, p, nullptr, nullptr)); break;
+        case BufferKind::Sorted: check(wc_download_cells(h, nullptr, nullptr, nullptr, p, nullptr)); break;
+        case BufferKind::NeighbourCounts:
+            check(wc_download_cells(h, nullptr, nullptr, nullptr, nullptr, p));
+            break;
+        default: throw Error(WC_ERR_INVALID, "getUints: not a uint buffer");
+    }
+    if (num_items >= 0 && (size_t)num_items < out.size()) out.resize((size_t)num_items);
+    return out;
+}
+
+void printParticles(Buffer particle_buffer, int n, float bin_size) {
+    const std::vector<Particle> particles = getParticles(particle_buffer, n);
+    for (size_t i = 0; i < particles.size(); i++) {
+        const Particle& p = particles[i];
+        log("p=<%f, %f, %f>, v=<%f, %f, %f>, d=%f, pr=%f, c=<%d, %d, %d>\n", p.position.x,
+            p.position.y, p.position.z, p.velocity.x, p.velocity.y, p.velocity.z, p.density,
+            p.pressure, (int)(p.position.x / bin_size), (int)(p.position.y / bin_size),
+            (int)(p.position.z / bin_size));
+    }
+}
+
+}  // namespace util
+}  // namespace core
