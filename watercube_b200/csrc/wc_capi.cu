@@ -252,8 +252,8 @@ int sort_reorder_phase(wc_handle* h, bool timed, int n_in, int n_sorted) {
     }
     if (h->group_start) {  // cut the owned rows into <= 32-particle groups for the gathers
         const int row0 = h->slab ? G : 0, row1 = h->slab ? (h->Lz - 1) * G : h->Lz * G;
-        k_build_groups<<<1, 1024, 0, h->stream>>>(h->offsets, G, row0, row1, h->group_start,
-                                                  h->group_row, h->num_groups);
+        k_build_groups<<<div_up(row1 - row0, 1024), 1024, 0, h->stream>>>(
+            h->offsets, G, row0, row1, h->group_start, h->group_row, h->num_groups);
         WC_CHECK_LAUNCH(h);
     }
     if (timed && (rc = record(h, 3))) return rc;
@@ -465,7 +465,7 @@ int wc_create(const wc_params* p, wc_handle** out) {
     // extra scan states (slab): ghost-low, ghost-high tables; the two migrant compactions
     const size_t xbytes[4] = {scan_state_bytes(G2), scan_state_bytes(G2), scan_state_bytes(capz),
                               scan_state_bytes(capz)};
-    h->arena_bytes = counts_bytes + status_bytes + 256;
+    h->arena_bytes = counts_bytes + status_bytes + 256;  // last 256: tile counter, num_groups
     const size_t x_off0 = h->arena_bytes;
     if (slab) h->arena_bytes += xbytes[0] + xbytes[1] + xbytes[2] + xbytes[3] + 256;
 
@@ -495,8 +495,6 @@ int wc_create(const wc_params* p, wc_handle** out) {
         const size_t groups = (size_t)h->groups_cap;
         WC_ALLOC(h->group_start, groups * sizeof(uint32_t));
         WC_ALLOC(h->group_row, groups * sizeof(uint32_t));
-        WC_ALLOC(h->num_groups, 256);
-        cudaMemsetAsync(h->num_groups, 0, 256, h->stream);
         if (p->neighbour_list_words >= 0) {
             h->nbr_cap_words = p->neighbour_list_words > 0 ? p->neighbour_list_words : 32;
             WC_ALLOC(h->nbr_idx, groups * h->nbr_cap_words * 32 * sizeof(uint32_t));
@@ -511,6 +509,7 @@ int wc_create(const wc_params* p, wc_handle** out) {
     h->counts = (uint32_t*)h->arena;
     h->scan_status = (unsigned long long*)((char*)h->arena + counts_bytes);
     h->scan_counter = (unsigned int*)((char*)h->arena + counts_bytes + status_bytes);
+    h->num_groups = (uint32_t*)((char*)h->arena + counts_bytes + status_bytes + 128);
     if (slab) {
         size_t off = x_off0;
         for (int k = 0; k < 4; k++) {
@@ -590,7 +589,6 @@ int wc_destroy(wc_handle* h) {
     cudaFree(h->nbr_words);
     cudaFree(h->group_start);
     cudaFree(h->group_row);
-    cudaFree(h->num_groups);
     for (int k = 0; k < 2; k++) {
         cudaFree(h->mig_out[k]);
         cudaFree(h->mig_in[k]);

@@ -34,19 +34,22 @@ constexpr int kDensityWarps = 8;           // warps (= groups) per block, densit
 constexpr int kUpdateWarps = 4;            // warps per block, update pass (10.6 KB stage each)
 constexpr int kChunk = 128;                // staged candidates per density batch (4 words)
 constexpr int kStageCap = kChunk + 32;     // one cull iteration can overshoot by < 32
-constexpr int kReplayWords = 8;            // list words re-staged per update batch
+constexpr int kReplayWords = 7;            // list words re-staged per update batch
 constexpr int kReplaySlots = kReplayWords * 32;
+constexpr int kDummySlot = kReplaySlots;   // 32 slots of a far-away, massless candidate
 constexpr float kFar = 1e18f;              // sentinel coordinate: never within h, no inf/NaN
 
 constexpr uint32_t kNoIndex = 0xFFFFFFFFu;       // padding slot in a staged / listed word
 constexpr uint32_t kListOverflow = 0xFFFFFFFFu;  // nbr_words value: list did not fit
 
 // ---------------------------------------------------------------------------------------
-// Group table.  One thread block walks the (y,z) rows of the offsets table in row order and
-// cuts each row's particle range into groups of <= 32: group_start[g] is the index of the
-// group's first particle in the sorted arrays, group_row[g] its row (z * G + y of the
-// table), *num_groups the total.  Rows [row_begin, row_end) are covered (slab mode skips the
-// two ghost layers).  Launch: <<<1, 1024>>>.
+// Group table.  Every block takes 1024 (y,z) rows of the offsets table and cuts each row's
+// particle range into groups of <= 32: group_start[g] is the index of the group's first
+// particle in the sorted arrays, group_row[g] its row (z * G + y of the table).  Blocks claim
+// their range of group numbers with one atomicAdd on *num_groups (zero at launch), so the
+// numbering is arbitrary between blocks -- nothing depends on it: a group's number only
+// selects its slice of the neighbour list, which the density and update passes of the same
+// step share.  Rows [row_begin, row_end) are covered (slab mode skips the two ghost layers).
 __global__ void __launch_bounds__(1024)
 k_build_groups(const uint32_t* __restrict__ offsets, int G, int row_begin, int row_end,
                uint32_t* __restrict__ group_start, uint32_t* __restrict__ group_row,
@@ -54,50 +57,43 @@ k_build_groups(const uint32_t* __restrict__ offsets, int G, int row_begin, int r
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_base = 0;
+    const int r0 = row_begin + blockIdx.x * 1024, r = r0 + tid;
+    uint32_t beg = 0, ng = 0;
+    if (r < row_end) {
+        beg = offsets[(size_t)r * G];
+        ng = (offsets[(size_t)(r + 1) * G] - beg + 31u) >> 5;
+    }
+    uint32_t incl = ng;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    for (int r0 = row_begin; r0 < row_end; r0 += 1024) {
-        const int r = r0 + tid;
-        uint32_t beg = 0, ng = 0;
-        if (r < row_end) {
-            beg = offsets[(size_t)r * G];
-            ng = (offsets[(size_t)(r + 1) * G] - beg + 31u) >> 5;
-        }
-        uint32_t incl = ng;
+    if (warp == 0) {
+        const uint32_t w = s_warp[lane];
+        uint32_t winc = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
         }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t w = s_warp[lane];
-            uint32_t winc = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= o) winc += t;
-            }
-            s_warp[lane] = winc - w;
-        }
-        __syncthreads();
-        const uint32_t g = s_base + s_warp[warp] + (incl - ng);
-        // the warp fills the groups of its 32 rows together (a row can hold many groups)
-        for (int src = 0; src < 32; src++) {
-            const uint32_t n_src = __shfl_sync(0xffffffffu, ng, src);
-            const uint32_t g_src = __shfl_sync(0xffffffffu, g, src);
-            const uint32_t b_src = __shfl_sync(0xffffffffu, beg, src);
-            for (uint32_t k = lane; k < n_src; k += 32) {
-                group_start[g_src + k] = b_src + 32u * k;
-                group_row[g_src + k] = (uint32_t)(r0 + warp * 32 + src);
-            }
-        }
-        __syncthreads();
-        if (tid == 1023) s_base = g + ng;
-        __syncthreads();
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_base = winc ? atomicAdd(num_groups, winc) : 0u;
     }
-    if (tid == 0) *num_groups = s_base;
+    __syncthreads();
+    const uint32_t g = s_base + s_warp[warp] + (incl - ng);
+    // the warp fills the groups of its 32 rows together (a row can hold many groups)
+    for (int src = 0; src < 32; src++) {
+        const uint32_t n_src = __shfl_sync(0xffffffffu, ng, src);
+        const uint32_t g_src = __shfl_sync(0xffffffffu, g, src);
+        const uint32_t b_src = __shfl_sync(0xffffffffu, beg, src);
+        for (uint32_t k = lane; k < n_src; k += 32) {
+            group_start[g_src + k] = b_src + 32u * k;
+            group_row[g_src + k] = (uint32_t)(r0 + warp * 32 + src);
+        }
+    }
 }
 
 // Upper bound of the number of groups for n particles in `rows` rows.
@@ -167,6 +163,7 @@ struct alignas(16) DensityStage {
     __device__ __forceinline__ void put(int slot, float4 q, uint32_t j_, const float4*) {
         x[slot] = q.x, y[slot] = q.y, z[slot] = q.z, j[slot] = j_;
     }
+    __device__ __forceinline__ void init(int) {}
     __device__ __forceinline__ void pad(int slot) {
         x[slot] = kFar, y[slot] = kFar, z[slot] = kFar, j[slot] = kNoIndex;
     }
@@ -181,12 +178,20 @@ struct alignas(16) DensityStage {
 
 // Update pass: a = (x, y, z, 1/rho), b = (vx, vy, vz, P); mask[w * 32 + lane] = the bits of
 // word w accepted by `lane`.  Sized for a replay batch; the no-list path uses the first
-// kStageCap slots in batches of kChunk.
+// kStageCap slots in batches of kChunk.  Slots [kDummySlot, kDummySlot + 32) hold a far-away
+// candidate with 1/rho = 0 whose pair force is exactly zero (what a lane evaluates when it
+// has no accepted bit left), and mask word kReplayWords is a zero terminator row (init()
+// writes both once per warp).
 struct alignas(16) UpdateStage {
-    float4 a[kReplaySlots];
-    float4 b[kReplaySlots];
-    uint32_t mask[kReplayWords * 32];
+    float4 a[kReplaySlots + 32];
+    float4 b[kReplaySlots + 32];
+    uint32_t mask[(kReplayWords + 1) * 32];
     uint32_t self_seq[32];
+    __device__ __forceinline__ void init(int lane) {
+        a[kDummySlot + lane] = make_float4(kFar, kFar, kFar, 0.0f);
+        b[kDummySlot + lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        mask[kReplayWords * 32 + lane] = 0u;
+    }
     __device__ __forceinline__ void put(int slot, float4 q, uint32_t j_, const float4* vel_pres) {
         q.w = __frcp_rn(q.w);  // the pair force only needs 1/rho_j
         a[slot] = q;
@@ -298,26 +303,34 @@ struct UpdateAcc {
         Fvz = fmaf(wv, qb.z - v.z, Fvz);
     }
 
-    // Every lane walks its own accepted bits of st.mask[0, nw) -- one flat loop over the
-    // whole batch, so lanes only wait for each other at the batch's end.
-    __device__ __forceinline__ void walk(const UpdateStage& st, int nw, const SphConsts& c,
+    // Every lane walks its own accepted bits of the staged mask words [0, nwb) -- one flat
+    // loop over the whole batch, two pairs per iteration, so lanes only wait for each other
+    // at the batch's end.  The lane keeps the word it is draining (m) and the next one (mn,
+    // prefetched) in registers, so moving on to the next word is branch-free and its
+    // shared-memory load is off the critical path; a pick that finds no bit (empty word, or
+    // lane finished) evaluates the dummy candidate, whose pair force is exactly zero.
+    // Mask rows [nwb, kReplayWords] must be zero.
+    __device__ __forceinline__ void walk(const UpdateStage& st, int nwb, const SphConsts& c,
                                          float4 p, float4 v) {
-        const int lane = threadIdx.x & 31;
-        int n = 0;
-#pragma unroll
-        for (int w = 0; w < kReplayWords; w++)
-            if (w < nw) n += __popc(st.mask[w * 32 + lane]);
-        const int nmax = __reduce_max_sync(0xffffffffu, n);
-        int w = -1;
-        unsigned m = 0u;
-        for (int it = 0; it < nmax; it++) {
-            if (it < n) {
-                while (m == 0u) m = st.mask[++w * 32 + lane];  // it < n: a set bit remains
-                const int pos = 31 - __clz((int)m);
-                m ^= 1u << pos;
-                const int slot = w * 32 + pos;
-                pair(c, p, v, st.a[slot], st.b[slot]);
+        const uint32_t* mrow = st.mask + (threadIdx.x & 31);
+        unsigned m = mrow[0], mn = mrow[32];
+        int w = 0;
+        auto pick = [&]() -> int {
+            if (m == 0u) {
+                m = mn;
+                w = min(w + 1, kReplayWords);
+                mn = mrow[min(w + 1, kReplayWords) * 32];
             }
+            const int pos = 31 - __clz((int)m);
+            const int slot = m ? w * 32 + pos : kDummySlot;
+            m &= ~(0x80000000u >> __clz((int)m));  // m == 0 stays 0 (shift by 32 gives 0)
+            return slot;
+        };
+        while (__any_sync(0xffffffffu, (m | mn) != 0u || w + 2 < nwb)) {
+            const int sa = pick(), sb = pick();
+            const float4 qa0 = st.a[sa], qb0 = st.b[sa], qa1 = st.a[sb], qb1 = st.b[sb];
+            pair(c, p, v, qa0, qb0);
+            pair(c, p, v, qa1, qb1);
         }
     }
 
@@ -339,6 +352,7 @@ struct UpdateAcc {
             words_used++;
             st.mask[w * 32 + lane] = mk;
         }
+        for (int w = nw; w < kReplayWords; w++) st.mask[w * 32 + lane] = 0u;
         __syncwarp();
         walk(st, nw, c, p, v);
     }
@@ -369,6 +383,7 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
     const float Tcull = c.T * 1.0001f;  // conservative: rounding in the box distance
     const float Teff = valid ? c.T : -1.0f;
     st.self_seq[lane] = kNoIndex;
+    st.init(lane);
     __syncwarp();
 
     // the nine slices (density.comp:95-101: rows outside the grid are skipped)
@@ -381,19 +396,10 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
             send = offsets[rowbase + gg.x1 + 1];
         }
     }
-    int s = 0, cnt = 0;
-    uint32_t j0 = __shfl_sync(full, sbeg, 0), end = __shfl_sync(full, send, 0);
-    bool done = false;
-    while (true) {
-        while (!done && j0 >= end) {
-            if (++s == 9) {
-                done = true;
-            } else {
-                j0 = __shfl_sync(full, sbeg, s);
-                end = __shfl_sync(full, send, s);
-            }
-        }
-        if (!done) {
+    int cnt = 0;
+    for (int s = 0; s < 9; s++) {
+        const uint32_t end = __shfl_sync(full, send, s);
+        for (uint32_t j0 = __shfl_sync(full, sbeg, s); j0 < end; j0 += 32) {
             // cull 32 candidates against the targets' box grown by h
             const uint32_t j = j0 + lane;
             const bool ok = j < end;
@@ -402,7 +408,7 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
             const float ex = fmaxf(fmaxf(bx0 - q.x, q.x - bx1), 0.0f);
             const float ey = fmaxf(fmaxf(by0 - q.y, q.y - by1), 0.0f);
             const float ez = fmaxf(fmaxf(bz0 - q.z, q.z - bz1), 0.0f);
-            const bool keep = ok && (ex * ex + ey * ey + ez * ez < Tcull);
+            const bool keep = ex * ex + ey * ey + ez * ez < Tcull;  // false for the kFar filler
             const unsigned km = __ballot_sync(full, keep);
             if (keep) {
                 const int slot = cnt + __popc(km & lt);
@@ -410,25 +416,24 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
                 if (j - wfirst < 32u) st.self_seq[j - wfirst] = acc.words_used * 32u + (uint32_t)slot;
             }
             cnt += __popc(km);
-            j0 += 32;
-        }
-        if (cnt >= kChunk || (done && cnt > 0)) {
-            int count = kChunk;
-            if (cnt < kChunk) {  // final partial batch: pad to a multiple of 32
-                count = (cnt + 31) & ~31;
-                if (cnt + lane < count) st.pad(cnt + lane);
-            }
-            __syncwarp();
-            acc.process(st, count, c, p, v, Teff);
-            __syncwarp();
-            const int left = cnt - min(cnt, kChunk);  // move the (< 32) leftovers to the front
-            if (left > 0) {
-                st.move(lane, kChunk + lane, lane < left);
+            if (cnt >= kChunk) {
                 __syncwarp();
+                acc.process(st, kChunk, c, p, v, Teff);
+                __syncwarp();
+                cnt -= kChunk;  // move the (< 32) leftovers to the front
+                if (cnt > 0) {
+                    st.move(lane, kChunk + lane, lane < cnt);
+                    __syncwarp();
+                }
             }
-            cnt = left;
         }
-        if (done && cnt == 0) break;
+    }
+    if (cnt > 0) {  // final partial batch: pad to a multiple of 32
+        const int count = (cnt + 31) & ~31;
+        if (cnt + lane < count) st.pad(cnt + lane);
+        __syncwarp();
+        acc.process(st, count, c, p, v, Teff);
+        __syncwarp();
     }
 }
 
@@ -539,15 +544,18 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
     } else {
         const uint32_t* widx = list.idx + (size_t)x.g * list.cap_words * 32 + lane;
         const uint32_t* wmask = list.mask + (size_t)x.g * list.cap_words * 32 + lane;
+        st.init(lane);
         for (uint32_t w0 = 0; w0 < nw; w0 += kReplayWords) {
             uint32_t jj[kReplayWords];
 #pragma unroll
             for (int u = 0; u < kReplayWords; u++) {
                 jj[u] = kNoIndex;
+                uint32_t mk = 0u;
                 if (w0 + u < nw) {
                     jj[u] = widx[(size_t)(w0 + u) * 32];
-                    st.mask[u * 32 + lane] = wmask[(size_t)(w0 + u) * 32];
+                    mk = wmask[(size_t)(w0 + u) * 32];
                 }
+                st.mask[u * 32 + lane] = mk;
             }
 #pragma unroll
             for (int u = 0; u < kReplayWords; u++) {
