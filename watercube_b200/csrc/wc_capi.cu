@@ -105,8 +105,7 @@ struct wc_handle {
     int nbr_cap_words = 0;
     bool nbr_valid = false;
     // group table of the tiled gather kernels (wc_sph_tile.cuh k_build_groups)
-    uint32_t* group_start = nullptr;
-    uint32_t* group_row = nullptr;
+    uint4* groups = nullptr;
     uint32_t* num_groups = nullptr;
     int groups_cap = 0;
 
@@ -250,10 +249,10 @@ int sort_reorder_phase(wc_handle* h, bool timed, int n_in, int n_sorted) {
             h->vel[1] + h->Cg, h->perm, h->zbase, (uint32_t)h->Cg);
         WC_CHECK_LAUNCH(h);
     }
-    if (h->group_start) {  // cut the owned rows into <= 32-particle groups for the gathers
+    if (h->groups) {  // cut the owned rows into <= 32-particle groups for the gathers
         const int row0 = h->slab ? G : 0, row1 = h->slab ? (h->Lz - 1) * G : h->Lz * G;
         k_build_groups<<<div_up(row1 - row0, 1024), 1024, 0, h->stream>>>(
-            h->offsets, G, row0, row1, h->group_start, h->group_row, h->num_groups);
+            h->offsets, G, row0, row1, h->groups, h->num_groups);
         WC_CHECK_LAUNCH(h);
     }
     if (timed && (rc = record(h, 3))) return rc;
@@ -263,7 +262,7 @@ int sort_reorder_phase(wc_handle* h, bool timed, int n_in, int n_sorted) {
 }
 
 GroupTable group_table(const wc_handle* h) {
-    return GroupTable{h->group_start, h->group_row, h->num_groups,
+    return GroupTable{h->groups, h->num_groups,
                       max_groups(h->n, (long long)h->Lz * h->p.grid_res)};
 }
 
@@ -493,8 +492,7 @@ int wc_create(const wc_params* p, wc_handle** out) {
     if (!(p->flags & WC_FLAG_SIMPLE_KERNELS)) {
         h->groups_cap = max_groups(cap, (long long)h->Lz * p->grid_res);
         const size_t groups = (size_t)h->groups_cap;
-        WC_ALLOC(h->group_start, groups * sizeof(uint32_t));
-        WC_ALLOC(h->group_row, groups * sizeof(uint32_t));
+        WC_ALLOC(h->groups, (groups + 64) * sizeof(uint4));  // + launch-bound round-up
         if (p->neighbour_list_words >= 0) {
             h->nbr_cap_words = p->neighbour_list_words > 0 ? p->neighbour_list_words : 32;
             WC_ALLOC(h->nbr_idx, groups * h->nbr_cap_words * 32 * sizeof(uint32_t));
@@ -587,8 +585,7 @@ int wc_destroy(wc_handle* h) {
     cudaFree(h->nbr_idx);
     cudaFree(h->nbr_mask);
     cudaFree(h->nbr_words);
-    cudaFree(h->group_start);
-    cudaFree(h->group_row);
+    cudaFree(h->groups);
     for (int k = 0; k < 2; k++) {
         cudaFree(h->mig_out[k]);
         cudaFree(h->mig_in[k]);

@@ -33,10 +33,11 @@ namespace wc {
 constexpr int kDensityWarps = 8;           // warps (= groups) per block, density pass
 constexpr int kUpdateWarps = 4;            // warps per block, update pass (10.6 KB stage each)
 constexpr int kChunk = 128;                // staged candidates per density batch (4 words)
-constexpr int kStageCap = kChunk + 32;     // one cull iteration can overshoot by < 32
+constexpr int kCullDepth = 4;              // density pass: cull loads in flight per lane
+constexpr int kRing = 256;                 // density stage: ring of kChunk + 32 * kCullDepth slots
+constexpr int kStageCap = kChunk + 32;     // no-list update path: linear stage, depth 1
 constexpr int kReplayWords = 7;            // list words re-staged per update batch
 constexpr int kReplaySlots = kReplayWords * 32;
-constexpr int kDummySlot = kReplaySlots;   // 32 slots of a far-away, massless candidate
 constexpr float kFar = 1e18f;              // sentinel coordinate: never within h, no inf/NaN
 
 constexpr uint32_t kNoIndex = 0xFFFFFFFFu;       // padding slot in a staged / listed word
@@ -44,25 +45,25 @@ constexpr uint32_t kListOverflow = 0xFFFFFFFFu;  // nbr_words value: list did no
 
 // ---------------------------------------------------------------------------------------
 // Group table.  Every block takes 1024 (y,z) rows of the offsets table and cuts each row's
-// particle range into groups of <= 32: group_start[g] is the index of the group's first
-// particle in the sorted arrays, group_row[g] its row (z * G + y of the table).  Blocks claim
+// particle range into groups of <= 32: groups[g] = {index of the group's first particle in
+// the sorted arrays, its row (z * G + y of the table), its particle count, 0}.  Blocks claim
 // their range of group numbers with one atomicAdd on *num_groups (zero at launch), so the
 // numbering is arbitrary between blocks -- nothing depends on it: a group's number only
 // selects its slice of the neighbour list, which the density and update passes of the same
 // step share.  Rows [row_begin, row_end) are covered (slab mode skips the two ghost layers).
 __global__ void __launch_bounds__(1024)
 k_build_groups(const uint32_t* __restrict__ offsets, int G, int row_begin, int row_end,
-               uint32_t* __restrict__ group_start, uint32_t* __restrict__ group_row,
-               uint32_t* __restrict__ num_groups) {
+               uint4* __restrict__ groups, uint32_t* __restrict__ num_groups) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r0 = row_begin + blockIdx.x * 1024, r = r0 + tid;
-    uint32_t beg = 0, ng = 0;
+    uint32_t beg = 0, cnt = 0;
     if (r < row_end) {
         beg = offsets[(size_t)r * G];
-        ng = (offsets[(size_t)(r + 1) * G] - beg + 31u) >> 5;
+        cnt = offsets[(size_t)(r + 1) * G] - beg;
     }
+    const uint32_t ng = (cnt + 31u) >> 5;
     uint32_t incl = ng;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -86,13 +87,12 @@ k_build_groups(const uint32_t* __restrict__ offsets, int G, int row_begin, int r
     const uint32_t g = s_base + s_warp[warp] + (incl - ng);
     // the warp fills the groups of its 32 rows together (a row can hold many groups)
     for (int src = 0; src < 32; src++) {
-        const uint32_t n_src = __shfl_sync(0xffffffffu, ng, src);
+        const uint32_t n_src = __shfl_sync(0xffffffffu, cnt, src);
         const uint32_t g_src = __shfl_sync(0xffffffffu, g, src);
         const uint32_t b_src = __shfl_sync(0xffffffffu, beg, src);
-        for (uint32_t k = lane; k < n_src; k += 32) {
-            group_start[g_src + k] = b_src + 32u * k;
-            group_row[g_src + k] = (uint32_t)(r0 + warp * 32 + src);
-        }
+        for (uint32_t k = lane; 32u * k < n_src; k += 32)
+            groups[g_src + k] = make_uint4(b_src + 32u * k, (uint32_t)(r0 + warp * 32 + src),
+                                           min(32u, n_src - 32u * k), 0u);
     }
 }
 
@@ -155,10 +155,12 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
 // appears in the warp's candidate sequence, recorded when it is staged (density.comp:110:
 // the particle itself is not a neighbour, so its bit is cleared from the masks).
 struct alignas(16) DensityStage {
-    float x[kStageCap];
-    float y[kStageCap];
-    float z[kStageCap];
-    uint32_t j[kStageCap];
+    static constexpr int kDepth = kCullDepth;
+    static constexpr int kWrap = kRing - 1;  // ring: batches start at slot 0 or kChunk
+    float x[kRing];
+    float y[kRing];
+    float z[kRing];
+    uint32_t j[kRing];
     uint32_t self_seq[32];
     __device__ __forceinline__ void put(int slot, float4 q, uint32_t j_, const float4*) {
         x[slot] = q.x, y[slot] = q.y, z[slot] = q.z, j[slot] = j_;
@@ -167,31 +169,21 @@ struct alignas(16) DensityStage {
     __device__ __forceinline__ void pad(int slot) {
         x[slot] = kFar, y[slot] = kFar, z[slot] = kFar, j[slot] = kNoIndex;
     }
-    __device__ __forceinline__ void move(int dst, int src, bool mv) {
-        float tx = 0, ty = 0, tz = 0;
-        uint32_t tj = 0;
-        if (mv) tx = x[src], ty = y[src], tz = z[src], tj = j[src];
-        __syncwarp();
-        if (mv) x[dst] = tx, y[dst] = ty, z[dst] = tz, j[dst] = tj;
-    }
 };
+static_assert(kRing == 2 * kChunk && kChunk + 32 * kCullDepth <= kRing, "ring sizing");
 
 // Update pass: a = (x, y, z, 1/rho), b = (vx, vy, vz, P); mask[w * 32 + lane] = the bits of
-// word w accepted by `lane`.  Sized for a replay batch; the no-list path uses the first
-// kStageCap slots in batches of kChunk.  Slots [kDummySlot, kDummySlot + 32) hold a far-away
-// candidate with 1/rho = 0 whose pair force is exactly zero (what a lane evaluates when it
-// has no accepted bit left), and mask word kReplayWords is a zero terminator row (init()
-// writes both once per warp).
+// word w accepted by `lane`, row kReplayWords is a zero terminator (init() writes it once
+// per warp).  Sized for a replay batch; the no-list path uses the first kStageCap slots in
+// batches of kChunk.
 struct alignas(16) UpdateStage {
-    float4 a[kReplaySlots + 32];
-    float4 b[kReplaySlots + 32];
+    static constexpr int kDepth = 1;
+    static constexpr int kWrap = 0;  // linear stage: leftovers are moved to the front
+    float4 a[kReplaySlots];
+    float4 b[kReplaySlots];  // walk() relies on b directly following a
     uint32_t mask[(kReplayWords + 1) * 32];
     uint32_t self_seq[32];
-    __device__ __forceinline__ void init(int lane) {
-        a[kDummySlot + lane] = make_float4(kFar, kFar, kFar, 0.0f);
-        b[kDummySlot + lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        mask[kReplayWords * 32 + lane] = 0u;
-    }
+    __device__ __forceinline__ void init(int lane) { mask[kReplayWords * 32 + lane] = 0u; }
     __device__ __forceinline__ void put(int slot, float4 q, uint32_t j_, const float4* vel_pres) {
         q.w = __frcp_rn(q.w);  // the pair force only needs 1/rho_j
         a[slot] = q;
@@ -229,14 +221,14 @@ struct DensityAcc {
     uint32_t* mask_out = nullptr;
     int cap_words = 0;
 
-    // Runs this lane's target over stage[0, count); count is a multiple of 32.
-    __device__ __forceinline__ void process(const DensityStage& st, int count, const SphConsts& c,
-                                            float4 p, float4, float Teff) {
+    // Runs this lane's target over stage[head, head + count); count is a multiple of 32.
+    __device__ __forceinline__ void process(const DensityStage& st, int head, int count,
+                                            const SphConsts& c, float4 p, float4, float Teff) {
         const int lane = threadIdx.x & 31;
         const uint32_t self_seq = st.self_seq[lane];
         const f32x2 PX = pack2(p.x, p.x), PY = pack2(p.y, p.y), PZ = pack2(p.z, p.z);
         const f32x2 H2 = pack2(c.h2, c.h2);
-        for (int k0 = 0; k0 < count; k0 += 32) {
+        for (int k0 = head; k0 < head + count; k0 += 32) {
             unsigned mk = 0u;
 #pragma unroll
             for (int q = 0; q < 8; q++) {
@@ -288,17 +280,18 @@ struct UpdateAcc {
     float Fpx = 0, Fpy = 0, Fpz = 0, Fvx = 0, Fvy = 0, Fvz = 0;
     uint32_t words_used = 0;  // words of the candidate sequence processed so far (no-list path)
 
-    // One accepted pair of update.comp:174-187.
+    // One accepted pair of update.comp:174-187; `on` = false turns the pair into a no-op
+    // (its operands are then stale registers).
     __device__ __forceinline__ void pair(const SphConsts& c, float4 p, float4 v, float4 qa,
-                                         float4 qb) {
+                                         float4 qb, bool on) {
         const float rx = p.x - qa.x, ry = p.y - qa.y, rz = p.z - qa.z;
         const float d2 = dist2(rx, ry, rz);
         const float inv_d = rsqrt_approx(fmaxf(d2, 1e-32f));  // Q7: dist == 0 -> r/d adds 0
         const float hd = c.h - d2 * inv_d;
         const float S = (v.w + qb.w) * qa.w;                   // 2 * (Pi+Pj)/(2 rho_j)
-        const float w = S > 0.0f ? (S * (hd * hd)) * inv_d : 0.0f;  // Q9
+        const float w = (on && S > 0.0f) ? (S * (hd * hd)) * inv_d : 0.0f;  // Q9
         Fpx = fmaf(w, rx, Fpx), Fpy = fmaf(w, ry, Fpy), Fpz = fmaf(w, rz, Fpz);
-        const float wv = hd * qa.w;                            // update.comp:186-187
+        const float wv = on ? hd * qa.w : 0.0f;                // update.comp:186-187
         Fvx = fmaf(wv, qb.x - v.x, Fvx), Fvy = fmaf(wv, qb.y - v.y, Fvy),
         Fvz = fmaf(wv, qb.z - v.z, Fvz);
     }
@@ -306,37 +299,47 @@ struct UpdateAcc {
     // Every lane walks its own accepted bits of the staged mask words [0, nwb) -- one flat
     // loop over the whole batch, two pairs per iteration, so lanes only wait for each other
     // at the batch's end.  The lane keeps the word it is draining (m) and the next one (mn,
-    // prefetched) in registers, so moving on to the next word is branch-free and its
-    // shared-memory load is off the critical path; a pick that finds no bit (empty word, or
-    // lane finished) evaluates the dummy candidate, whose pair force is exactly zero.
+    // prefetched) in registers, so moving on to the next word is a few predicated
+    // instructions and its shared-memory load is off the critical path; a pick that finds
+    // no bit (empty word, or lane finished) loads nothing and adds zero.
     // Mask rows [nwb, kReplayWords] must be zero.
     __device__ __forceinline__ void walk(const UpdateStage& st, int nwb, const SphConsts& c,
                                          float4 p, float4 v) {
-        const uint32_t* mrow = st.mask + (threadIdx.x & 31);
-        unsigned m = mrow[0], mn = mrow[32];
-        int w = 0;
-        auto pick = [&]() -> int {
+        const int lane = threadIdx.x & 31;
+        const uint32_t* mptr = st.mask + lane;
+        const uint32_t* const mend = mptr + 32 * nwb;  // a zero row
+        unsigned m = mptr[0], mn = (nwb > 1) ? mptr[32] : 0u;
+        mptr = (nwb > 2) ? mptr + 64 : mend;
+        const float4* abase = st.a;  // slot 0 of the word being drained
+        float4 qa0 = make_float4(0, 0, 0, 0), qb0 = qa0, qa1 = qa0, qb1 = qa0;
+        auto pick = [&](float4& qa, float4& qb) -> bool {
             if (m == 0u) {
                 m = mn;
-                w = min(w + 1, kReplayWords);
-                mn = mrow[min(w + 1, kReplayWords) * 32];
+                abase += 32;
+                mn = *mptr;
+                mptr = (mptr == mend) ? mend : mptr + 32;
             }
-            const int pos = 31 - __clz((int)m);
-            const int slot = m ? w * 32 + pos : kDummySlot;
-            m &= ~(0x80000000u >> __clz((int)m));  // m == 0 stays 0 (shift by 32 gives 0)
-            return slot;
+            const bool on = m != 0u;
+            const int lz = __clz((int)m);  // 32 when no bit is left
+            if (on) {
+                const float4* q = abase + (31 - lz);
+                qa = q[0];
+                qb = q[kReplaySlots];
+            }
+            m &= ~(0x80000000u >> (lz & 31));
+            return on;
         };
-        while (__any_sync(0xffffffffu, (m | mn) != 0u || w + 2 < nwb)) {
-            const int sa = pick(), sb = pick();
-            const float4 qa0 = st.a[sa], qb0 = st.b[sa], qa1 = st.a[sb], qb1 = st.b[sb];
-            pair(c, p, v, qa0, qb0);
-            pair(c, p, v, qa1, qb1);
+        while (__any_sync(0xffffffffu, (m | mn) != 0u || mptr != mend)) {
+            const bool on0 = pick(qa0, qb0);
+            const bool on1 = pick(qa1, qb1);
+            pair(c, p, v, qa0, qb0, on0);
+            pair(c, p, v, qa1, qb1, on1);
         }
     }
 
     // No-list path: phase 1 = distance test only -> one bit per staged candidate, then walk.
-    __device__ __forceinline__ void process(UpdateStage& st, int count, const SphConsts& c,
-                                            float4 p, float4 v, float Teff) {
+    __device__ __forceinline__ void process(UpdateStage& st, int /*head = 0*/, int count,
+                                            const SphConsts& c, float4 p, float4 v, float Teff) {
         const int lane = threadIdx.x & 31;
         const uint32_t self_seq = st.self_seq[lane];
         const int nw = count >> 5;
@@ -396,32 +399,43 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
             send = offsets[rowbase + gg.x1 + 1];
         }
     }
-    int cnt = 0;
+    constexpr int kDepth = Stage::kDepth;
+    int cnt = 0, head = 0;  // pending candidates are stage[head, head + cnt) (mod ring)
     for (int s = 0; s < 9; s++) {
         const uint32_t end = __shfl_sync(full, send, s);
-        for (uint32_t j0 = __shfl_sync(full, sbeg, s); j0 < end; j0 += 32) {
-            // cull 32 candidates against the targets' box grown by h
-            const uint32_t j = j0 + lane;
-            const bool ok = j < end;
-            float4 q = make_float4(kFar, kFar, kFar, 0.0f);
-            if (ok) q = pos_rho[j];
-            const float ex = fmaxf(fmaxf(bx0 - q.x, q.x - bx1), 0.0f);
-            const float ey = fmaxf(fmaxf(by0 - q.y, q.y - by1), 0.0f);
-            const float ez = fmaxf(fmaxf(bz0 - q.z, q.z - bz1), 0.0f);
-            const bool keep = ex * ex + ey * ey + ez * ez < Tcull;  // false for the kFar filler
-            const unsigned km = __ballot_sync(full, keep);
-            if (keep) {
-                const int slot = cnt + __popc(km & lt);
-                st.put(slot, q, j, vel_pres);
-                if (j - wfirst < 32u) st.self_seq[j - wfirst] = acc.words_used * 32u + (uint32_t)slot;
+        for (uint32_t j0 = __shfl_sync(full, sbeg, s); j0 < end; j0 += 32 * kDepth) {
+            // kDepth x 32 candidates in flight, then culled against the targets' box grown
+            // by h, 32 at a time, and ballot-compacted behind the pending ones
+            float4 q[kDepth];
+#pragma unroll
+            for (int k = 0; k < kDepth; k++) {
+                const uint32_t j = j0 + 32 * k + lane;
+                q[k] = make_float4(kFar, kFar, kFar, 0.0f);
+                if (j < end) q[k] = pos_rho[j];
             }
-            cnt += __popc(km);
+#pragma unroll
+            for (int k = 0; k < kDepth; k++) {
+                const uint32_t j = j0 + 32 * k + lane;
+                const float ex = fmaxf(fmaxf(bx0 - q[k].x, q[k].x - bx1), 0.0f);
+                const float ey = fmaxf(fmaxf(by0 - q[k].y, q[k].y - by1), 0.0f);
+                const float ez = fmaxf(fmaxf(bz0 - q[k].z, q[k].z - bz1), 0.0f);
+                const bool keep = ex * ex + ey * ey + ez * ez < Tcull;  // false for the filler
+                const unsigned km = __ballot_sync(full, keep);
+                if (keep) {
+                    const int at = cnt + __popc(km & lt);
+                    st.put(Stage::kWrap ? ((head + at) & Stage::kWrap) : at, q[k], j, vel_pres);
+                    if (j - wfirst < 32u) st.self_seq[j - wfirst] = acc.words_used * 32u + (uint32_t)at;
+                }
+                cnt += __popc(km);
+            }
             if (cnt >= kChunk) {
                 __syncwarp();
-                acc.process(st, kChunk, c, p, v, Teff);
+                acc.process(st, head, kChunk, c, p, v, Teff);
                 __syncwarp();
-                cnt -= kChunk;  // move the (< 32) leftovers to the front
-                if (cnt > 0) {
+                cnt -= kChunk;
+                if constexpr (Stage::kWrap != 0) {
+                    head ^= kChunk;  // the ring's other half
+                } else if (cnt > 0) {  // linear stage: move the (< 32) leftovers to the front
                     st.move(lane, kChunk + lane, lane < cnt);
                     __syncwarp();
                 }
@@ -430,9 +444,9 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
     }
     if (cnt > 0) {  // final partial batch: pad to a multiple of 32
         const int count = (cnt + 31) & ~31;
-        if (cnt + lane < count) st.pad(cnt + lane);
+        if (cnt + lane < count) st.pad(head + cnt + lane);
         __syncwarp();
-        acc.process(st, count, c, p, v, Teff);
+        acc.process(st, head, count, c, p, v, Teff);
         __syncwarp();
     }
 }
@@ -448,32 +462,27 @@ struct GroupCtx {
     GroupGeom gg;
 };
 
-__device__ __forceinline__ GroupCtx group_prologue(const float4* pos_rho,
-                                                   const uint32_t* __restrict__ offsets,
-                                                   const SphConsts& c,
-                                                   const uint32_t* __restrict__ group_start,
-                                                   const uint32_t* __restrict__ group_row,
+__device__ __forceinline__ GroupCtx group_prologue(const float4* pos_rho, const SphConsts& c,
+                                                   const uint4* __restrict__ groups,
                                                    const uint32_t* __restrict__ num_groups,
                                                    int warps_per_block, float4* p_out) {
     GroupCtx x;
     const int lane = threadIdx.x & 31;
     x.g = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const uint4 rec = groups[x.g];  // the table is allocated for the launch bound; may be stale
     x.active = (uint32_t)x.g < *num_groups;
     x.valid = false;
     x.t = x.i = 0;
     x.wfirst = 0;
     *p_out = make_float4(0, 0, 0, 0);
     if (!x.active) return x;
-    const uint32_t i0 = group_start[x.g];
-    x.wfirst = i0;
-    const uint32_t row = group_row[x.g];  // every group has at least one particle
+    x.wfirst = rec.x;
     const int G = c.G;
-    x.gg.rz = (int)(row / (uint32_t)G);
-    x.gg.ry = (int)(row - (uint32_t)x.gg.rz * (uint32_t)G);
-    const uint32_t row_end = offsets[((size_t)row + 1) * G];
-    const int cnt = (int)min(32u, row_end - i0);
+    x.gg.rz = (int)(rec.y / (uint32_t)G);
+    x.gg.ry = (int)(rec.y - (uint32_t)x.gg.rz * (uint32_t)G);
+    const int cnt = (int)rec.z;  // >= 1
     x.valid = lane < cnt;
-    x.i = (int)i0 + lane;
+    x.i = (int)rec.x + lane;
     x.t = x.i - c.first;
     float4 p = make_float4(0, 0, 0, 0);
     if (x.valid) p = pos_rho[x.i];
@@ -487,17 +496,15 @@ __device__ __forceinline__ GroupCtx group_prologue(const float4* pos_rho,
 }
 
 template <bool kDebug>
-__global__ void __launch_bounds__(kDensityWarps * 32)
+__global__ void __launch_bounds__(kDensityWarps * 32, 4)
 k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
                const uint32_t* __restrict__ offsets, SphConsts c,
-               const uint32_t* __restrict__ group_start, const uint32_t* __restrict__ group_row,
-               const uint32_t* __restrict__ num_groups, uint32_t* __restrict__ neighbour_counts,
-               NbrList list) {
+               const uint4* __restrict__ groups, const uint32_t* __restrict__ num_groups,
+               uint32_t* __restrict__ neighbour_counts, NbrList list) {
     __shared__ DensityStage s_stage[kDensityWarps];
     const int lane = threadIdx.x & 31;
     float4 p;
-    const GroupCtx x = group_prologue(pos_rho, offsets, c, group_start, group_row, num_groups,
-                                      kDensityWarps, &p);
+    const GroupCtx x = group_prologue(pos_rho, c, groups, num_groups, kDensityWarps, &p);
     if (!x.active) return;
     DensityAcc<kDebug> acc;
     if (list.idx) {
@@ -521,17 +528,16 @@ k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
 // words; without one (list.idx == nullptr, or this group overflowed its list) it runs the
 // cull + distance test itself.
 template <bool kDebug>
-__global__ void __launch_bounds__(kUpdateWarps * 32)
+__global__ void __launch_bounds__(kUpdateWarps * 32, 6)
 k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel_pres,
               const uint32_t* __restrict__ offsets, SphConsts c,
-              const uint32_t* __restrict__ group_start, const uint32_t* __restrict__ group_row,
-              const uint32_t* __restrict__ num_groups, float4* __restrict__ pos_out, float4* __restrict__ vel_out,
+              const uint4* __restrict__ groups, const uint32_t* __restrict__ num_groups,
+              float4* __restrict__ pos_out, float4* __restrict__ vel_out,
               float4* __restrict__ forces, NbrList list) {
     __shared__ UpdateStage s_stage[kUpdateWarps];
     const int lane = threadIdx.x & 31;
     float4 p;
-    const GroupCtx x = group_prologue(pos_rho, offsets, c, group_start, group_row, num_groups,
-                                      kUpdateWarps, &p);
+    const GroupCtx x = group_prologue(pos_rho, c, groups, num_groups, kUpdateWarps, &p);
     if (!x.active) return;
     float4 v = make_float4(0, 0, 0, 0);
     if (x.valid) v = vel_pres[x.i];
@@ -582,8 +588,7 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
 }
 
 struct GroupTable {
-    const uint32_t* start;
-    const uint32_t* row;
+    const uint4* groups;
     const uint32_t* count;  // device scalar
     int max_groups;         // launch bound (>= *count)
 };
@@ -596,10 +601,10 @@ inline void launch_density_tile(float4* pos_rho, float4* vel_pres, const uint32_
     const int blocks = blocks_for(gt.max_groups, kDensityWarps);
     if (neighbour_counts)
         k_density_tile<true><<<blocks, kDensityWarps * 32, 0, stream>>>(
-            pos_rho, vel_pres, offsets, c, gt.start, gt.row, gt.count, neighbour_counts, list);
+            pos_rho, vel_pres, offsets, c, gt.groups, gt.count, neighbour_counts, list);
     else
         k_density_tile<false><<<blocks, kDensityWarps * 32, 0, stream>>>(
-            pos_rho, vel_pres, offsets, c, gt.start, gt.row, gt.count, nullptr, list);
+            pos_rho, vel_pres, offsets, c, gt.groups, gt.count, nullptr, list);
 }
 
 inline void launch_update_tile(const float4* pos_rho, const float4* vel_pres,
@@ -609,11 +614,11 @@ inline void launch_update_tile(const float4* pos_rho, const float4* vel_pres,
     const int blocks = blocks_for(gt.max_groups, kUpdateWarps);
     if (forces)
         k_update_tile<true><<<blocks, kUpdateWarps * 32, 0, stream>>>(
-            pos_rho, vel_pres, offsets, c, gt.start, gt.row, gt.count, pos_out, vel_out, forces,
+            pos_rho, vel_pres, offsets, c, gt.groups, gt.count, pos_out, vel_out, forces,
             list);
     else
         k_update_tile<false><<<blocks, kUpdateWarps * 32, 0, stream>>>(
-            pos_rho, vel_pres, offsets, c, gt.start, gt.row, gt.count, pos_out, vel_out, nullptr,
+            pos_rho, vel_pres, offsets, c, gt.groups, gt.count, pos_out, vel_out, nullptr,
             list);
 }
 
