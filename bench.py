@@ -37,6 +37,8 @@ FRAME_DT = 1.0 / 60.0
 # compulsory DRAM bytes per particle-update, by stage (sum = 168 B).
 ALGO_BYTES = {"hash_count": 16, "scan": 0, "reorder": 64, "density": 24, "update": 64}
 ALGO_BYTES_STEP = 168
+KERNEL_NAMES = {"hash_count": "k_hash_count", "scan": "k_scan", "reorder": "k_reorder",
+                "density": "k_density_tile", "update": "k_update_tile"}
 L2_BYTES = 126 * 1024 * 1024
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
 
@@ -309,11 +311,9 @@ def run_b200(args):
     per_stage = {k: v / args.steps for k, v in stage_ms.items()}
     dom = max(per_stage, key=per_stage.get)
     achieved = ALGO_BYTES[dom] * n / (per_stage[dom] * 1e-3) / 1e9
-    kernel_names = {"hash_count": "k_hash_count", "scan": "k_scan", "reorder": "k_reorder",
-                    "density": "k_density", "update": "k_update"}
-    roofline = {"bound": "hbm", "kernel": kernel_names[dom], "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": KERNEL_NAMES[dom], "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
-                "traffic": recorded_traffic(kernel_names[dom], n),
+                "traffic": recorded_traffic(KERNEL_NAMES[dom], n),
                 "algorithmic_bytes_per_particle": ALGO_BYTES[dom], "peak_source": peak_src,
                 "ms_per_launch": per_stage[dom]}
     step_gbs = ALGO_BYTES_STEP * n / (ms_per_step * 1e-3) / 1e9

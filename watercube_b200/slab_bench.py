@@ -1,0 +1,205 @@
+"""bench.py's multi-GPU leg: z-slab decomposed dam break, one rank per GPU (torchrun).
+
+Weak scaling: every rank owns about --particles-per-gpu particles (8M x 8 GPUs = BASELINE's
+64M configuration).  The scene is the jittered dam-break lattice of scenes.dam_break; a rank
+generates only the lattice planes that can fall into its slab (the lattice index is z-major),
+so set-up cost does not grow with the world size.  Slab cuts give equal particle counts
+(slab.slab_cuts over the global z-layer histogram).
+
+Exchange: torch.distributed P2P over NCCL between slab neighbours only (layer counts, halo
+positions, halo density/pressure/velocity, migrants) -- see watercube_b200/slab.py.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+from . import scenes, slab
+
+FRAME_DT = 1.0 / 60.0
+
+
+def _layer_hist_and_ranges(n, d, spacing, jitter, half, bin_size, grid_res, seed, chunk=1 << 22):
+    """Global z-layer histogram of the n-particle dam break from the z coordinates alone."""
+    hist = np.zeros(grid_res, np.int64)
+    for s0 in range(0, n, chunk):
+        idx = np.arange(s0, min(n, s0 + chunk), dtype=np.int64)
+        z = (idx // (d * d)).astype(np.float32) * spacing
+        z += scenes.hash_u01(3 * idx + 2, seed) * jitter - half
+        hist += np.bincount(slab.layer_of(z, bin_size, grid_res), minlength=grid_res)
+    return hist
+
+
+def make_rank_scene(n_total, rank, world, seed=0):
+    """-> (scene params, cuts, this rank's particles [m, 8])."""
+    radius = scenes.DEFAULT_RADIUS
+    size, grid_res = scenes.scaled_box(n_total, radius)
+    d = scenes.lattice_side(n_total)
+    spacing = np.float32(radius) * np.float32(scenes.DEFAULT_SPACING_FACTOR)
+    jitter = spacing * np.float32(0.5)
+    half = jitter / np.float32(2.0)
+    bin_size = np.float32(size) / np.float32(grid_res)
+    hist = _layer_hist_and_ranges(n_total, d, spacing, jitter, half, bin_size, grid_res, seed)
+    cuts = slab.slab_cuts(hist, world)
+    # lattice planes that can reach this rank's layers (jitter < one plane spacing)
+    z_lo, z_hi = cuts[rank] * float(bin_size), cuts[rank + 1] * float(bin_size)
+    p_lo = max(int(np.floor(z_lo / float(spacing))) - 1, 0)
+    p_hi = min(int(np.ceil(z_hi / float(spacing))) + 2, d)
+    i0, i1 = min(p_lo * d * d, n_total), min(p_hi * d * d, n_total)
+    out = []
+    chunk = 1 << 22
+    for s0 in range(i0, i1, chunk):
+        idx = np.arange(s0, min(i1, s0 + chunk), dtype=np.int64)
+        xyz = np.stack([idx % d, (idx // d) % d, idx // (d * d)], axis=1).astype(np.float32)
+        pos = xyz * spacing
+        for k in range(3):
+            pos[:, k] += scenes.hash_u01(3 * idx + k, seed) * jitter - half
+        lay = slab.layer_of(pos[:, 2], bin_size, grid_res)
+        keep = (lay >= cuts[rank]) & (lay < cuts[rank + 1])
+        part = np.zeros((int(keep.sum()), scenes.PARTICLE_FLOATS), np.float32)
+        part[:, 0:3] = pos[keep]
+        out.append(part)
+    mine = np.concatenate(out) if out else np.zeros((0, scenes.PARTICLE_FLOATS), np.float32)
+    params = dict(grid_res=int(grid_res), size=float(size), particle_radius=float(radius))
+    return params, cuts, hist, mine
+
+
+def run(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+
+    from . import capi
+    import bench  # the launching script: shared helpers (clock sampler, peaks, config)
+
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+
+    n_total = args.particles or args.particles_per_gpu * world
+    params, cuts, hist, mine = make_rank_scene(n_total, rank, world)
+    n_mine = mine.shape[0]
+    layer_max = int(hist.max())
+    cap = int(n_mine * 1.25) + 4 * layer_max + 1024
+    ghost_cap = int(layer_max * 1.5) + 1024
+    mig_cap = max(layer_max // 2, 65536)
+    flags = capi.FLAG_STAGE_TIMING
+    b = slab.CudaSlabBackend(params, cuts[rank], cuts[rank + 1], capacity=cap,
+                             ghost_capacity=ghost_cap, migrant_capacity=mig_cap, device=local,
+                             flags=flags, stream=stream.cuda_stream)
+    b.upload(mine)
+    drv = slab.SlabDriver(b, rank, world)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
+        slab.run_step(drv, FRAME_DT)
+    barrier()
+
+    sampler = bench.ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    launches0 = b.fluid.launch_count()
+    stage_ms = {k: 0.0 for k in capi.STAGES}
+    barrier()
+    t_wall0 = time.time()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        slab.run_step(drv, FRAME_DT)
+        for k, v in b.fluid.stage_times().items():
+            stage_ms[k] += v
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)       # device time, max over ranks
+    ms_per_step = float(ms.item()) / args.steps
+    launches = b.fluid.launch_count() - launches0
+    n_now = torch.tensor([b.num_particles], device="cuda", dtype=torch.int64)
+    dist.all_reduce(n_now)
+    assert int(n_now.item()) == n_total, (int(n_now.item()), n_total)  # nothing lost in migration
+    value = n_total / (ms_per_step * 1e-3)
+
+    # ---- e2e: every rank's slab goes host -> device and back every step
+    e2e = None
+    if not args.no_e2e:
+        cur = b.download(1)
+        h_in = torch.empty((cap, 8), dtype=torch.float32, pin_memory=True)
+        h_out = torch.empty((cap, 8), dtype=torch.float32, pin_memory=True)
+        n_cur = cur.shape[0]
+        h_in[:n_cur].copy_(torch.from_numpy(cur))
+        steps_e = max(3, min(args.steps, 10))
+        h2d = d2h = 0
+        barrier()
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(steps_e):
+            b.fluid.upload((h_in.data_ptr(), n_cur))
+            h2d += n_cur * 32
+            slab.run_step(drv, FRAME_DT)
+            n_cur = b.num_particles
+            b.fluid.download(1, out=(h_out.data_ptr(), n_cur))
+            d2h += n_cur * 32
+            h_in, h_out = h_out, h_in
+        ev1.record(stream)
+        barrier()
+        ms_e = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+        tot = torch.tensor([h2d, d2h], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tot)
+        ms_e_step = float(ms_e.item()) / steps_e
+        e2e = {"value": n_total / (ms_e_step * 1e-3), "unit": bench.UNIT, "ms_per_step": ms_e_step,
+               "h2d_bytes_per_step": int(tot[0].item()) // steps_e,
+               "d2h_bytes_per_step": int(tot[1].item()) // steps_e}
+    clocks = sampler.stop(t_wall0, t_wall1)
+
+    per_stage = {k: v / args.steps for k, v in stage_ms.items()}
+    stage_t = torch.tensor([per_stage[k] for k in capi.STAGES], device="cuda")
+    dist.all_reduce(stage_t, op=dist.ReduceOp.MAX)
+    per_stage = dict(zip(capi.STAGES, [float(x) for x in stage_t.tolist()]))
+    counts = [None] * world
+    dist.all_gather_object(counts, int(b.num_particles))
+    if rank == 0:
+        peak, peak_src = bench.peak_hbm()
+        dom = max(per_stage, key=per_stage.get)
+        n_rank_max = max(counts)
+        achieved = bench.ALGO_BYTES[dom] * n_rank_max / (per_stage[dom] * 1e-3) / 1e9
+        step_gbs = bench.ALGO_BYTES_STEP * n_total / world / (ms_per_step * 1e-3) / 1e9
+
+        class _Sc:  # what bench.workload_config reads
+            size, grid_res, particle_radius = params["size"], params["grid_res"], params["particle_radius"]
+
+        line = {
+            "metric": bench.METRIC, "value": value, "unit": bench.UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": bench.workload_config(args, _Sc, n_total, world, {
+                "l2": "per-rank working set > L2, no flush", "kernels": "tiled",
+                "slab_cuts": [int(c) for c in cuts], "particles_per_rank": counts,
+                "exchange": "NCCL P2P with slab neighbours: layer counts, halo positions, "
+                            "halo rho/P/velocity, migrants"}),
+            "stage_ms": per_stage,
+            "roofline": {"bound": "hbm", "kernel": bench.KERNEL_NAMES[dom], "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": bench.recorded_traffic(bench.KERNEL_NAMES[dom], n_rank_max),
+                         "algorithmic_bytes_per_particle": bench.ALGO_BYTES[dom],
+                         "peak_source": peak_src, "ms_per_launch": per_stage[dom],
+                         "note": "largest rank, per GPU"},
+            "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
+                              "frac": step_gbs / peak, "note": "per GPU, whole step incl. exchange"},
+            "clocks": clocks, "gpu_launches": int(launches) * world,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
