@@ -79,15 +79,34 @@ def peak_hbm():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(kernel_key, n):
-    """DRAM bytes per launch from the committed ncu capture (profiles/traffic.json), or None."""
+def recorded(kernel_key, n, field="dram_bytes"):
+    """Per-launch figure from the committed `ncu --set full` capture (profiles/traffic.json,
+    written by tools/make_traffic.py), or None when this kernel / size was not captured."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
         e = t.get(f"{kernel_key}@{n}")
-        return float(e["dram_bytes"]) if e else None
+        return float(e[field]) if e else None
     except Exception:
         return None
+
+
+def recorded_traffic(kernel_key, n):
+    return recorded(kernel_key, n, "dram_bytes")
+
+
+def issue_roofline(kernel_key, n, ms_per_launch, sm_mhz):
+    """How close the kernel runs to the SM instruction-issue ceiling: warp instructions per
+    launch (from the committed ncu capture) / duration, against 148 SMs x 4 schedulers x the
+    SM clock sampled during the run.  Explains why the HBM fraction is small."""
+    inst = recorded(kernel_key, n, "warp_inst")
+    if inst is None or not sm_mhz:
+        return None
+    peak = 148 * 4 * sm_mhz * 1e6
+    achieved = inst / (ms_per_launch * 1e-3)
+    return {"bound": "issue", "kernel": kernel_key, "achieved": achieved / 1e9, "peak": peak / 1e9,
+            "unit": "G warp-inst/s", "frac": achieved / peak,
+            "warp_inst_per_particle": inst / n}
 
 
 class ClockSampler:
@@ -331,6 +350,9 @@ def run_b200(args):
         "stage_ms": per_stage, "roofline": roofline, "roofline_step": roofline_step,
         "clocks": clocks, "gpu_launches": int(launches),
     }
+    ir = issue_roofline(KERNEL_NAMES[dom], n, per_stage[dom], clocks.get("sm_mhz"))
+    if ir:
+        line["issue_roofline"] = ir
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu_baseline:

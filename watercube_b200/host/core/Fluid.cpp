@@ -101,6 +101,12 @@ void Fluid::generateInitialParticles() {
     }
 }
 
+const std::vector<Particle>& Fluid::initialParticles() {
+    if (!user_particles_ && (int)initial_particles_.size() != num_particles_)
+        generateInitialParticles();
+    return initial_particles_;
+}
+
 FluidRef Fluid::setup() {
     util::log("creating fluid\n");
     if (handle_) {  // reset path (WaterCubeApp.cpp:81-88); the reference leaks its old buffers

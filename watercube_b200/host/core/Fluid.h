@@ -73,7 +73,8 @@ public:
     float kernelRadius() const { return derived_.kernel_radius; }
     float particleMass() const { return derived_.particle_mass; }
     int numBins() const { return derived_.num_bins; }
-    const std::vector<Particle>& initialParticlesRef() const { return initial_particles_; }
+    // The initial lattice (generated on first use; does not touch the device).
+    const std::vector<Particle>& initialParticles();
 
     static FluidRef create(const std::string& name) { return std::make_shared<Fluid>(name); }
 

@@ -3,6 +3,7 @@
 // time (quirk Q15: the app uses the wall clock), print conserved / statistical quantities.
 //
 //   wc_headless [--particles N] [--size S] [--grid G] [--steps K] [--device D] [--dump file]
+//               [--initial-only]   (write the initial lattice to --dump; no device needed)
 //
 // Exit code 0 on success, 2 when the native layer reports an error (e.g. no sm_100 device:
 // there is no CPU fallback).
@@ -20,6 +21,7 @@ int main(int argc, char** argv) {
     int n = 80000, grid = 21, steps = 100, device = 0;
     float size = 1.0f;
     const char* dump = nullptr;
+    bool initial_only = false;
     for (int i = 1; i < argc; i++) {
         auto next = [&](const char* flag) -> const char* {
             if (std::strcmp(argv[i], flag) != 0) return nullptr;
@@ -32,10 +34,21 @@ int main(int argc, char** argv) {
         else if (const char* v = next("--steps")) steps = std::atoi(v);
         else if (const char* v = next("--device")) device = std::atoi(v);
         else if (const char* v = next("--dump")) dump = v;
+        else if (std::strcmp(argv[i], "--initial-only") == 0) initial_only = true;
         else { std::fprintf(stderr, "unknown argument %s\n", argv[i]); return 1; }
     }
     try {
         FluidRef fluid = Fluid::create("fluid")->numParticles(n)->size(size)->gridRes(grid)->device(device);
+        if (initial_only) {
+            const std::vector<Particle>& init = fluid->initialParticles();
+            FILE* f = dump ? std::fopen(dump, "wb") : nullptr;
+            if (!f || std::fwrite(init.data(), sizeof(Particle), init.size(), f) != init.size()) {
+                std::fprintf(stderr, "cannot write the initial particles (--dump file)\n");
+                return 1;
+            }
+            std::fclose(f);
+            return 0;
+        }
         fluid->setup();  // WaterCubeApp.cpp:59-62
         const double frame = 1.0 / 60.0;
         const auto t0 = std::chrono::steady_clock::now();
