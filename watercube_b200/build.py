@@ -42,11 +42,13 @@ def needs_build() -> bool:
     return any(os.path.getmtime(f) > t for f in _inputs() if os.path.exists(f))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """defines / out: build a tuning variant (e.g. defines=["WC_REPLAY_WORDS=10"]) elsewhere."""
+    lib = out or LIB
+    if not force and not out and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB,
-           *[os.path.join(CSRC, s) for s in SOURCES]]
+    cmd = [_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []),
+           *[f"-D{d}" for d in defines], "-o", lib, *[os.path.join(CSRC, s) for s in SOURCES]]
     env = dict(os.environ)
     # the image exports CC/CXX wrappers that nvcc does not need; use the distro host compiler
     res = subprocess.run(cmd + ["-ccbin", "/usr/bin/g++"], env=env, capture_output=True, text=True)
@@ -55,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed")
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

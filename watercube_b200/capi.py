@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-LIB_PATH = os.path.join(_CSRC, "libwc_sph.so")
+# WC_SPH_LIB selects another build of the same library (kernel-tuning experiments only).
+LIB_PATH = os.environ.get("WC_SPH_LIB") or os.path.join(_CSRC, "libwc_sph.so")
 
 WC_OK, WC_ERR_INVALID, WC_ERR_NO_DEVICE, WC_ERR_CUDA, WC_ERR_CAPACITY = 0, 1, 2, 3, 4
 FLAG_DEBUG_OUTPUTS, FLAG_STAGE_TIMING, FLAG_SIMPLE_KERNELS = 1, 2, 4

@@ -30,13 +30,30 @@
 
 namespace wc {
 
-constexpr int kDensityWarps = 8;           // warps (= groups) per block, density pass
-constexpr int kUpdateWarps = 4;            // warps per block, update pass (10.6 KB stage each)
+#ifndef WC_DENSITY_WARPS
+#define WC_DENSITY_WARPS 8
+#endif
+#ifndef WC_DENSITY_MIN_BLOCKS
+#define WC_DENSITY_MIN_BLOCKS 4
+#endif
+constexpr int kDensityWarps = WC_DENSITY_WARPS;  // warps (= groups) per block, density pass
+#ifndef WC_UPDATE_WARPS
+#define WC_UPDATE_WARPS 4
+#endif
+// Tuning knobs (defaults from the sweep recorded in profiles/r01_variant_sweep.md: the update
+// pass prefers occupancy over batch size).
+#ifndef WC_REPLAY_WORDS
+#define WC_REPLAY_WORDS 5
+#endif
+#ifndef WC_UPDATE_MIN_BLOCKS
+#define WC_UPDATE_MIN_BLOCKS 8
+#endif
+constexpr int kUpdateWarps = WC_UPDATE_WARPS;  // warps per block, update pass (6 KB stage each)
 constexpr int kChunk = 128;                // staged candidates per density batch (4 words)
 constexpr int kCullDepth = 4;              // density pass: cull loads in flight per lane
 constexpr int kRing = 256;                 // density stage: ring of kChunk + 32 * kCullDepth slots
-constexpr int kStageCap = kChunk + 32;     // no-list update path: linear stage, depth 1
-constexpr int kReplayWords = 7;            // list words re-staged per update batch
+
+constexpr int kReplayWords = WC_REPLAY_WORDS;  // list words re-staged per update batch
 constexpr int kReplaySlots = kReplayWords * 32;
 constexpr float kFar = 1e18f;              // sentinel coordinate: never within h, no inf/NaN
 
@@ -155,6 +172,7 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
 // appears in the warp's candidate sequence, recorded when it is staged (density.comp:110:
 // the particle itself is not a neighbour, so its bit is cleared from the masks).
 struct alignas(16) DensityStage {
+    static constexpr int kBatch = kChunk;
     static constexpr int kDepth = kCullDepth;
     static constexpr int kWrap = kRing - 1;  // ring: batches start at slot 0 or kChunk
     float x[kRing];
@@ -174,9 +192,10 @@ static_assert(kRing == 2 * kChunk && kChunk + 32 * kCullDepth <= kRing, "ring si
 
 // Update pass: a = (x, y, z, 1/rho), b = (vx, vy, vz, P); mask[w * 32 + lane] = the bits of
 // word w accepted by `lane`, row kReplayWords is a zero terminator (init() writes it once
-// per warp).  Sized for a replay batch; the no-list path uses the first kStageCap slots in
-// batches of kChunk.
+// per warp).  Sized for a replay batch; the no-list path uses the first kBatch + 32 slots.
 struct alignas(16) UpdateStage {
+    // no-list path: linear stage of kBatch + 32 slots inside the replay buffers, depth 1
+    static constexpr int kBatch = (kReplayWords - 1) * 32 < kChunk ? (kReplayWords - 1) * 32 : kChunk;
     static constexpr int kDepth = 1;
     static constexpr int kWrap = 0;  // linear stage: leftovers are moved to the front
     float4 a[kReplaySlots];
@@ -197,7 +216,8 @@ struct alignas(16) UpdateStage {
         if (mv) a[dst] = ta, b[dst] = tb;
     }
 };
-static_assert(kStageCap <= kReplaySlots, "the no-list path stages into the replay buffers");
+static_assert(UpdateStage::kBatch >= 32 && UpdateStage::kBatch + 32 <= kReplaySlots,
+              "the no-list path stages into the replay buffers");
 
 // Neighbour list handed from the density pass to the update pass.  Layout:
 // [(group * cap_words + word) * 32 + lane], i.e. one coalesced 128-byte line per word, for
@@ -428,15 +448,15 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
                 }
                 cnt += __popc(km);
             }
-            if (cnt >= kChunk) {
+            if (cnt >= Stage::kBatch) {
                 __syncwarp();
-                acc.process(st, head, kChunk, c, p, v, Teff);
+                acc.process(st, head, Stage::kBatch, c, p, v, Teff);
                 __syncwarp();
-                cnt -= kChunk;
+                cnt -= Stage::kBatch;
                 if constexpr (Stage::kWrap != 0) {
-                    head ^= kChunk;  // the ring's other half
+                    head ^= Stage::kBatch;  // the ring's other half
                 } else if (cnt > 0) {  // linear stage: move the (< 32) leftovers to the front
-                    st.move(lane, kChunk + lane, lane < cnt);
+                    st.move(lane, Stage::kBatch + lane, lane < cnt);
                     __syncwarp();
                 }
             }
@@ -496,7 +516,7 @@ __device__ __forceinline__ GroupCtx group_prologue(const float4* pos_rho, const 
 }
 
 template <bool kDebug>
-__global__ void __launch_bounds__(kDensityWarps * 32, 4)
+__global__ void __launch_bounds__(kDensityWarps * 32, WC_DENSITY_MIN_BLOCKS)
 k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
                const uint32_t* __restrict__ offsets, SphConsts c,
                const uint4* __restrict__ groups, const uint32_t* __restrict__ num_groups,
@@ -528,13 +548,14 @@ k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
 // words; without one (list.idx == nullptr, or this group overflowed its list) it runs the
 // cull + distance test itself.
 template <bool kDebug>
-__global__ void __launch_bounds__(kUpdateWarps * 32, 6)
+__global__ void __launch_bounds__(kUpdateWarps * 32, WC_UPDATE_MIN_BLOCKS)
 k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel_pres,
               const uint32_t* __restrict__ offsets, SphConsts c,
               const uint4* __restrict__ groups, const uint32_t* __restrict__ num_groups,
               float4* __restrict__ pos_out, float4* __restrict__ vel_out,
               float4* __restrict__ forces, NbrList list) {
-    __shared__ UpdateStage s_stage[kUpdateWarps];
+    extern __shared__ __align__(16) unsigned char s_dyn[];  // kUpdateWarps stages (may exceed 48 KB)
+    UpdateStage* s_stage = reinterpret_cast<UpdateStage*>(s_dyn);
     const int lane = threadIdx.x & 31;
     float4 p;
     const GroupCtx x = group_prologue(pos_rho, c, groups, num_groups, kUpdateWarps, &p);
@@ -612,12 +633,19 @@ inline void launch_update_tile(const float4* pos_rho, const float4* vel_pres,
                                float4* pos_out, float4* vel_out, float4* forces, NbrList list,
                                cudaStream_t stream) {
     const int blocks = blocks_for(gt.max_groups, kUpdateWarps);
+    constexpr size_t smem = kUpdateWarps * sizeof(UpdateStage);
+    if (smem > 48 * 1024) {  // opt-in size; the attribute is per device, so set it per launch
+        if (forces)
+            cudaFuncSetAttribute(k_update_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        else
+            cudaFuncSetAttribute(k_update_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
     if (forces)
-        k_update_tile<true><<<blocks, kUpdateWarps * 32, 0, stream>>>(
+        k_update_tile<true><<<blocks, kUpdateWarps * 32, smem, stream>>>(
             pos_rho, vel_pres, offsets, c, gt.groups, gt.count, pos_out, vel_out, forces,
             list);
     else
-        k_update_tile<false><<<blocks, kUpdateWarps * 32, 0, stream>>>(
+        k_update_tile<false><<<blocks, kUpdateWarps * 32, smem, stream>>>(
             pos_rho, vel_pres, offsets, c, gt.groups, gt.count, pos_out, vel_out, nullptr,
             list);
 }
