@@ -75,8 +75,9 @@ typedef struct wc_params {
     int32_t device;         /* CUDA device ordinal */
     uint32_t flags;         /* WC_FLAG_* */
     int32_t neighbour_list_words; /* per 32-particle group: capacity of the density->update
-                               neighbour list in 32-candidate words; 0 = default (32),
-                               < 0 = no list (update repeats the search) */
+                               neighbour list in 32-candidate words; 0 = default (32..96,
+                               from the scene's mean number density), < 0 = no list
+                               (update repeats the search) */
     /* z-slab mode (multi-GPU, one handle per rank): this handle owns the global z-layers
      * [slab_z_begin, slab_z_end) of the grid.  Enabled when slab_ghost_capacity > 0;
      * `capacity` then bounds the OWNED particles.  See the wc_slab_* calls below. */
@@ -156,6 +157,11 @@ int wc_step(wc_handle* h, float frame_dt, const wc_step_params* sp);
 int wc_sort_only(wc_handle* h);                                      /* Sort::run, Sort.cpp:254 */
 int wc_density_only(wc_handle* h, const wc_step_params* sp);         /* Fluid.cpp:268 */
 int wc_update_only(wc_handle* h, float frame_dt, const wc_step_params* sp); /* Fluid.cpp:294 */
+
+/* Fluid::runAdvectProg (Fluid.cpp:326-337) on buffer 1, in place: advect.comp:20-59.  Dead in
+ * the reference (its call is commented out, Fluid.cpp:351); provided so every shader under
+ * assets/fluid has a counterpart.  Not part of wc_step. */
+int wc_advect_only(wc_handle* h, float frame_dt);
 
 /* util::getUints (util.cpp:65-71) for the sort outputs; any pointer may be NULL.
  * cell_ids[n], counts[num_bins], offsets[num_bins], sorted_perm[n], neighbour_counts[n]. */

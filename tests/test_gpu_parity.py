@@ -379,3 +379,16 @@ def test_update_only_after_upload_sorted_does_not_trust_stale_list(capi, oracle)
     ro = oracle.as_f32(ro)
     assert np.max(np.abs(F - rF)) <= RTOL_F * np.abs(rF).max()
     assert np.max(np.abs(out[:, 0:3] - ro[:, 0:3])) <= ULPS_X * ulp(sc.size)
+
+
+def test_advect_dead_pass_bit_exact(capi, oracle):
+    """advect.comp (never dispatched by the reference, Fluid.cpp:351): elementwise, so bit-exact."""
+    sc = scenes.dam_break(5000, seed=23)
+    rng = np.random.default_rng(23)
+    sc.particles[:, 4:7] = rng.uniform(-50, 50, (sc.n, 3)).astype(f32)
+    with gpu_fluid(capi, sc, 0) as fl:
+        fl.upload(sc.particles)
+        fl.advect_only(FRAME_DT)
+        got = fl.download(1)
+    ref = oracle.as_f32(oracle.advect(sc.particles, sc.size, f32(FRAME_DT) * f32(0.012)))
+    np.testing.assert_array_equal(got, ref)

@@ -32,7 +32,7 @@ EXPORTS = (
     "wc_download_forces", "wc_upload_sorted", "wc_device_ptrs", "wc_export_aos_device", "wc_sync",
     "wc_stage_times", "wc_launch_count", "wc_slab_get_view", "wc_slab_clear_recv",
     "wc_slab_sort_count", "wc_slab_sync_info", "wc_slab_reorder", "wc_slab_density",
-    "wc_slab_update",
+    "wc_slab_update", "wc_advect_only",
 )
 
 
@@ -119,6 +119,7 @@ def lib():
             "wc_sort_only": [vp],
             "wc_density_only": [vp, C.POINTER(StepParams)],
             "wc_update_only": [vp, f32, C.POINTER(StepParams)],
+            "wc_advect_only": [vp, f32],
             "wc_download_cells": [vp, vp, vp, vp, vp, vp],
             "wc_download_forces": [vp, vp],
             "wc_upload_sorted": [vp, vp, i32],
@@ -270,6 +271,10 @@ class Fluid:
 
     def update_only(self, frame_dt=1.0 / 60.0):
         check(lib().wc_update_only(self._h, float(frame_dt), C.byref(self.step_params)))
+
+    def advect_only(self, frame_dt=1.0 / 60.0):
+        """Fluid::runAdvectProg (dead in the reference, Fluid.cpp:351)"""
+        check(lib().wc_advect_only(self._h, float(frame_dt)))
 
     def sync(self):
         check(lib().wc_sync(self._h))

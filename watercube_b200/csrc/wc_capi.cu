@@ -251,7 +251,7 @@ int sort_reorder_phase(wc_handle* h, bool timed, int n_in, int n_sorted) {
     }
     if (h->groups) {  // cut the owned rows into <= 32-particle groups for the gathers
         const int row0 = h->slab ? G : 0, row1 = h->slab ? (h->Lz - 1) * G : h->Lz * G;
-        k_build_groups<<<div_up(row1 - row0, 1024), 1024, 0, h->stream>>>(
+        k_build_groups<<<div_up(row1 - row0, kGroupRows), kGroupRows, 0, h->stream>>>(
             h->offsets, G, row0, row1, h->groups, h->num_groups);
         WC_CHECK_LAUNCH(h);
     }
@@ -494,7 +494,15 @@ int wc_create(const wc_params* p, wc_handle** out) {
         const size_t groups = (size_t)h->groups_cap;
         WC_ALLOC(h->groups, (groups + 64) * sizeof(uint4));  // + launch-bound round-up
         if (p->neighbour_list_words >= 0) {
-            h->nbr_cap_words = p->neighbour_list_words > 0 ? p->neighbour_list_words : 32;
+            // Default capacity: ~3x the candidates a 32-particle group keeps at the scene's mean
+            // number density (box of its targets grown by h), between 32 and 96 words.  A group
+            // that overflows falls back to a fresh search in the update pass (still exact).
+            const double box = (double)p->size, hh = (double)d.kernel_radius, bs = (double)d.bin_size;
+            const double kept = (double)cap / (box * box * box) * (1.6 * bs + 2 * hh) *
+                                (bs + 2 * hh) * (bs + 2 * hh);
+            int words = (int)std::ceil(3.0 * kept / 32.0);
+            words = words < 32 ? 32 : (words > 96 ? 96 : words);
+            h->nbr_cap_words = p->neighbour_list_words > 0 ? p->neighbour_list_words : words;
             WC_ALLOC(h->nbr_idx, groups * h->nbr_cap_words * 32 * sizeof(uint32_t));
             WC_ALLOC(h->nbr_mask, groups * h->nbr_cap_words * 32 * sizeof(uint32_t));
             WC_ALLOC(h->nbr_words, groups * sizeof(uint32_t));
@@ -704,6 +712,19 @@ int wc_update_only(wc_handle* h, float frame_dt, const wc_step_params* sp) {
     WC_CUDA(cudaSetDevice(h->p.device));
     h->have_times = false;
     return run_update(h, *sp, frame_dt);
+}
+
+int wc_advect_only(wc_handle* h, float frame_dt) {
+    if (!h) return fail(WC_ERR_INVALID, "handle is NULL");
+    if (h->slab) return fail(WC_ERR_INVALID, "wc_advect_only is not available on slab handles");
+    WC_CUDA(cudaSetDevice(h->p.device));
+    h->have_times = false;
+    if (h->n > 0) {
+        k_advect<<<div_up(h->n, 256), 256, 0, h->stream>>>(h->pos[0], h->vel[0], h->n, h->p.size,
+                                                           frame_dt * h->p.time_scale);
+        WC_CHECK_LAUNCH(h);
+    }
+    return WC_OK;
 }
 
 int wc_download_cells(wc_handle* h, uint32_t* cell_ids, uint32_t* counts, uint32_t* offsets,

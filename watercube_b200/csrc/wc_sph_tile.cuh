@@ -61,20 +61,23 @@ constexpr uint32_t kNoIndex = 0xFFFFFFFFu;       // padding slot in a staged / l
 constexpr uint32_t kListOverflow = 0xFFFFFFFFu;  // nbr_words value: list did not fit
 
 // ---------------------------------------------------------------------------------------
-// Group table.  Every block takes 1024 (y,z) rows of the offsets table and cuts each row's
+// Group table.  Every block takes kGroupRows (y,z) rows of the offsets table and cuts each row's
 // particle range into groups of <= 32: groups[g] = {index of the group's first particle in
 // the sorted arrays, its row (z * G + y of the table), its particle count, 0}.  Blocks claim
 // their range of group numbers with one atomicAdd on *num_groups (zero at launch), so the
 // numbering is arbitrary between blocks -- nothing depends on it: a group's number only
 // selects its slice of the neighbour list, which the density and update passes of the same
 // step share.  Rows [row_begin, row_end) are covered (slab mode skips the two ghost layers).
-__global__ void __launch_bounds__(1024)
+constexpr int kGroupRows = 128;
+__global__ void __launch_bounds__(kGroupRows)
 k_build_groups(const uint32_t* __restrict__ offsets, int G, int row_begin, int row_end,
                uint4* __restrict__ groups, uint32_t* __restrict__ num_groups) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r0 = row_begin + blockIdx.x * 1024, r = r0 + tid;
+    const int r0 = row_begin + blockIdx.x * kGroupRows, r = r0 + tid;
+    if (tid < 32) s_warp[tid] = 0;
+    __syncthreads();
     uint32_t beg = 0, cnt = 0;
     if (r < row_end) {
         beg = offsets[(size_t)r * G];
@@ -168,9 +171,10 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Stages.  self_seq[t] = position (word * 32 + bit) at which target lane t's own particle
-// appears in the warp's candidate sequence, recorded when it is staged (density.comp:110:
-// the particle itself is not a neighbour, so its bit is cleared from the masks).
+// Stages.  A target's own particle is one of the staged candidates: it passes the distance
+// test with d2 = 0, which is exactly the m * poly6(0) term the density starts from
+// (density.comp:92), and its pair force is exactly zero (r = 0, v_j - v_i = 0), so it stays in
+// the accept masks; only the neighbour COUNT subtracts it (density.comp:110, j != i).
 struct alignas(16) DensityStage {
     static constexpr int kBatch = kChunk;
     static constexpr int kDepth = kCullDepth;
@@ -179,7 +183,6 @@ struct alignas(16) DensityStage {
     float y[kRing];
     float z[kRing];
     uint32_t j[kRing];
-    uint32_t self_seq[32];
     __device__ __forceinline__ void put(int slot, float4 q, uint32_t j_, const float4*) {
         x[slot] = q.x, y[slot] = q.y, z[slot] = q.z, j[slot] = j_;
     }
@@ -201,7 +204,6 @@ struct alignas(16) UpdateStage {
     float4 a[kReplaySlots];
     float4 b[kReplaySlots];  // walk() relies on b directly following a
     uint32_t mask[(kReplayWords + 1) * 32];
-    uint32_t self_seq[32];
     __device__ __forceinline__ void init(int lane) { mask[kReplayWords * 32 + lane] = 0u; }
     __device__ __forceinline__ void put(int slot, float4 q, uint32_t j_, const float4* vel_pres) {
         q.w = __frcp_rn(q.w);  // the pair force only needs 1/rho_j
@@ -245,7 +247,6 @@ struct DensityAcc {
     __device__ __forceinline__ void process(const DensityStage& st, int head, int count,
                                             const SphConsts& c, float4 p, float4, float Teff) {
         const int lane = threadIdx.x & 31;
-        const uint32_t self_seq = st.self_seq[lane];
         const f32x2 PX = pack2(p.x, p.x), PY = pack2(p.y, p.y), PZ = pack2(p.z, p.z);
         const f32x2 H2 = pack2(c.h2, c.h2);
         for (int k0 = head; k0 < head + count; k0 += 32) {
@@ -279,7 +280,6 @@ struct DensityAcc {
                     }
                 }
             }
-            if (words_used == (self_seq >> 5)) mk &= ~(1u << (self_seq & 31u));  // density.comp:110
             if (kDebug) nn += (uint32_t)__popc(mk);
             if (idx_out) {
                 if (words_used < (uint32_t)cap_words) {
@@ -361,7 +361,6 @@ struct UpdateAcc {
     __device__ __forceinline__ void process(UpdateStage& st, int /*head = 0*/, int count,
                                             const SphConsts& c, float4 p, float4 v, float Teff) {
         const int lane = threadIdx.x & 31;
-        const uint32_t self_seq = st.self_seq[lane];
         const int nw = count >> 5;
         for (int w = 0; w < nw; w++) {
             unsigned mk = 0u;
@@ -371,7 +370,6 @@ struct UpdateAcc {
                 const float d2 = dist2(p.x - q.x, p.y - q.y, p.z - q.z);
                 mk |= (d2 < Teff) ? (1u << k) : 0u;
             }
-            if (words_used == (self_seq >> 5)) mk &= ~(1u << (self_seq & 31u));
             words_used++;
             st.mask[w * 32 + lane] = mk;
         }
@@ -392,7 +390,7 @@ template <typename Stage, typename Acc>
 __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4* vel_pres,
                                              const uint32_t* __restrict__ offsets,
                                              const SphConsts& c, Stage& st, Acc& acc, bool valid,
-                                             uint32_t wfirst, const GroupGeom& gg, float4 p,
+                                             const GroupGeom& gg, float4 p,
                                              float4 v) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -405,7 +403,6 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
     const float bz0 = warp_min_f(p.z, box), bz1 = warp_max_f(p.z, box);
     const float Tcull = c.T * 1.0001f;  // conservative: rounding in the box distance
     const float Teff = valid ? c.T : -1.0f;
-    st.self_seq[lane] = kNoIndex;
     st.init(lane);
     __syncwarp();
 
@@ -444,7 +441,6 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
                 if (keep) {
                     const int at = cnt + __popc(km & lt);
                     st.put(Stage::kWrap ? ((head + at) & Stage::kWrap) : at, q[k], j, vel_pres);
-                    if (j - wfirst < 32u) st.self_seq[j - wfirst] = acc.words_used * 32u + (uint32_t)at;
                 }
                 cnt += __popc(km);
             }
@@ -478,7 +474,6 @@ struct GroupCtx {
     int i;           // this lane's particle index in the candidate arrays
     bool active;     // the warp has a group
     bool valid;      // this lane has a target
-    uint32_t wfirst;
     GroupGeom gg;
 };
 
@@ -493,10 +488,8 @@ __device__ __forceinline__ GroupCtx group_prologue(const float4* pos_rho, const 
     x.active = (uint32_t)x.g < *num_groups;
     x.valid = false;
     x.t = x.i = 0;
-    x.wfirst = 0;
     *p_out = make_float4(0, 0, 0, 0);
     if (!x.active) return x;
-    x.wfirst = rec.x;
     const int G = c.G;
     x.gg.rz = (int)(rec.y / (uint32_t)G);
     x.gg.ry = (int)(rec.y - (uint32_t)x.gg.rz * (uint32_t)G);
@@ -532,7 +525,7 @@ k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
         acc.mask_out = list.mask + (size_t)x.g * list.cap_words * 32 + lane;
         acc.cap_words = list.cap_words;
     }
-    gather_group(pos_rho, vel_pres, offsets, c, s_stage[threadIdx.x >> 5], acc, x.valid, x.wfirst,
+    gather_group(pos_rho, vel_pres, offsets, c, s_stage[threadIdx.x >> 5], acc, x.valid,
                  x.gg, p, make_float4(0, 0, 0, 0));
     if (list.idx && lane == 0) list.words[x.g] = acc.overflow ? kListOverflow : acc.words_used;
     if (!x.valid) return;
@@ -541,7 +534,10 @@ k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
     // In place like density.comp:135; the gather only reads x,y,z, which do not change.
     reinterpret_cast<float*>(pos_rho)[4 * (size_t)x.i + 3] = rho;
     reinterpret_cast<float*>(vel_pres)[4 * (size_t)x.i + 3] = pres;
-    if (kDebug) neighbour_counts[x.t] = acc.nn;  // the self pair's bit is already cleared
+    if (kDebug) {  // the self pair was accepted iff the particle's own d2 is 0 (finite position)
+        const bool self = dist2(p.x - p.x, p.y - p.y, p.z - p.z) < c.T;
+        neighbour_counts[x.t] = acc.nn - (self ? 1u : 0u);
+    }
 }
 
 // update.comp:134-232.  With a valid neighbour list the warp replays the density pass's
@@ -567,7 +563,7 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
     uint32_t nw = kListOverflow;
     if (list.idx) nw = list.words[x.g];
     if (nw == kListOverflow) {
-        gather_group(pos_rho, vel_pres, offsets, c, st, acc, x.valid, x.wfirst, x.gg, p, v);
+        gather_group(pos_rho, vel_pres, offsets, c, st, acc, x.valid, x.gg, p, v);
     } else {
         const uint32_t* widx = list.idx + (size_t)x.g * list.cap_words * 32 + lane;
         const uint32_t* wmask = list.mask + (size_t)x.g * list.cap_words * 32 + lane;

@@ -121,6 +121,25 @@ __device__ __forceinline__ void pair_force(const SphConsts& c, float rx, float r
     Fvz = fmaf(wv, vj.z - vi.z, Fvz);
 }
 
+// advect.comp:20-59 (dead in the reference: its dispatch is commented out, Fluid.cpp:351).
+// Position-only Euler step with the 0.01 border; only the position is stored (advect.comp:58).
+__global__ void __launch_bounds__(256)
+k_advect(float4* __restrict__ pos_rho, const float4* __restrict__ vel_pres, int n, float size,
+         float dt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pos_rho[i];
+    const float4 v = vel_pres[i];
+    const float border = 0.01f, top = size - border;
+    float x = __fadd_rn(p.x, __fmul_rn(v.x, dt));
+    float y = __fadd_rn(p.y, __fmul_rn(v.y, dt));
+    float z = __fadd_rn(p.z, __fmul_rn(v.z, dt));
+    x = x < border ? border : (x > top ? top : x);
+    y = y < border ? border : (y > top ? top : y);
+    z = z < border ? border : (z > top ? top : z);
+    pos_rho[i] = make_float4(x, y, z, p.w);
+}
+
 template <bool kDebug>
 __global__ void __launch_bounds__(128)
 k_density_v1(float4* pos_rho, float4* __restrict__ vel_pres, const uint32_t* __restrict__ offsets,
