@@ -1,9 +1,14 @@
 #!/bin/bash
-# Multi-GPU visit: NCCL parity test + slab bench.  usage: tools/gpu_multi.sh <ngpus> <tag>
-N=${1:-2}; TAG=${2:-x}
+# Multi-GPU visit: NCCL parity test + slab bench.  usage: tools/gpu_multi.sh <ngpus> <tag> [ppg...]
+N=${1:-2}; TAG=${2:-x}; shift 2
+PPGS=${@:-8000000}
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/gpus_$TAG.txt
 timeout 900 python -m pytest tests/test_slab_gpu.py -m gpu -x -q -k nccl > gpurun_out/pytest_nccl_$TAG.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_nccl_$TAG.log; tail -3 gpurun_out/pytest_nccl_$TAG.log
-for PPG in 1000000 8000000; do
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 --particles-per-gpu $PPG > gpurun_out/bench_n${N}_${PPG}_$TAG.json 2> gpurun_out/bench_n${N}_${PPG}_$TAG.err; echo "rc=$?"; cat gpurun_out/bench_n${N}_${PPG}_$TAG.json; tail -5 gpurun_out/bench_n${N}_${PPG}_$TAG.err
+for PPG in $PPGS; do
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 --particles-per-gpu $PPG > gpurun_out/bench_n${N}_${PPG}_$TAG.json 2> gpurun_out/bench_n${N}_${PPG}_$TAG.err; echo "rc=$?"; python -c "
+import json,sys
+d=json.loads(open('gpurun_out/bench_n${N}_${PPG}_$TAG.json').read().strip().splitlines()[-1])
+print('N',d['n_gpus'],'particles',d['config']['particles'],'ms',round(d['ms_per_step'],3),'G/s',round(d['value']/1e9,3),{k:round(v,3) for k,v in d['stage_ms'].items()}, 'e2e', round(d.get('e2e',{}).get('value',0)/1e9,3), d['config']['particles_per_rank'])
+"; grep -v "OMP_NUM_THREADS\|^\*\*\*\|^$\|NCCL version" gpurun_out/bench_n${N}_${PPG}_$TAG.err | tail -5
 done

@@ -567,6 +567,7 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
     } else {
         const uint32_t* widx = list.idx + (size_t)x.g * list.cap_words * 32 + lane;
         const uint32_t* wmask = list.mask + (size_t)x.g * list.cap_words * 32 + lane;
+        const uint32_t first_target = (uint32_t)(x.i - lane);
         st.init(lane);
         for (uint32_t w0 = 0; w0 < nw; w0 += kReplayWords) {
             uint32_t jj[kReplayWords];
@@ -588,6 +589,14 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
                     st.a[u * 32 + lane] = qa;
                     st.b[u * 32 + lane] = vel_pres[jj[u]];
                 }
+            }
+            __syncwarp();
+            // a listed candidate that is one of this group's own targets: drop that target's
+            // self pair (it would add exactly zero; this only saves the evaluation)
+#pragma unroll
+            for (int u = 0; u < kReplayWords; u++) {
+                const uint32_t t = jj[u] - first_target;
+                if (t < 32u) atomicAnd(&st.mask[u * 32 + t], ~(1u << lane));
             }
             __syncwarp();
             acc.walk(st, (int)min((uint32_t)kReplayWords, nw - w0), c, p, v);
