@@ -204,7 +204,7 @@ typedef struct wc_slab_view {
     void* pos_rho_sorted;  /* float4 buffer 2; owned particles start at index owned_first */
     void* vel_pres_sorted;
     uint64_t mig_bytes;    /* size of one migrant message: 32-byte header + capacity * 32 */
-    uint64_t lc_bytes;     /* size of one layer-count message: 4 * (1 + grid_res^2) */
+    uint64_t lc_bytes;     /* size of one layer-count message: 4 * (2 + grid_res^2) */
     int32_t owned_first;   /* = slab_ghost_capacity */
     int32_t reserved;
 } wc_slab_view;
@@ -219,6 +219,30 @@ int wc_slab_sync_info(wc_handle* h, int32_t info[8]);
 int wc_slab_reorder(wc_handle* h);
 int wc_slab_density(wc_handle* h, const wc_step_params* sp);
 int wc_slab_update(wc_handle* h, float frame_dt, const wc_step_params* sp);
+
+/* ---- peer-memory exchange: the slab step without a host-driven transport ----------------
+ * After the two neighbours of a slab handle are attached, the wc_slab_* phase calls move the
+ * four per-step messages themselves: each phase copies its output into the neighbour's
+ * buffers (mapped peer memory, NVLink) on the handle's stream and raises a step counter in
+ * the neighbour's signal array; the consuming phase first queues a one-thread kernel that
+ * waits for that counter.  The caller then simply issues, per step,
+ *   wc_slab_sort_count, wc_slab_sync_info, wc_slab_reorder, wc_slab_density, wc_slab_update
+ * on every rank, with no exchange of its own.  Attach before the first step.
+ *   same process (tests, one process driving several GPUs): wc_slab_peer_attach
+ *   one process per GPU: wc_slab_ipc_export -> ship the 456-byte blob to the neighbour by any
+ *   means (bench.py uses torch.distributed's object all-gather) -> wc_slab_peer_open.
+ * A missing neighbour is simply not attached (and wc_slab_clear_recv zeroes its buffers). */
+#define WC_IPC_HANDLE_BYTES 64
+typedef struct wc_slab_ipc {
+    /* cudaIpcMemHandle_t of: buffer 2 positions, buffer 2 velocities, mig_in[0], mig_in[1],
+     * lc_recv[0], lc_recv[1], signal array */
+    unsigned char mem[7][WC_IPC_HANDLE_BYTES];
+    int32_t device;
+    int32_t ghost_capacity;
+} wc_slab_ipc;
+int wc_slab_ipc_export(wc_handle* h, wc_slab_ipc* out);
+int wc_slab_peer_open(wc_handle* h, int32_t direction, const wc_slab_ipc* peer);
+int wc_slab_peer_attach(wc_handle* h, int32_t direction, wc_handle* peer);
 
 /* Milliseconds per stage of the last wc_step (needs WC_FLAG_STAGE_TIMING; syncs). */
 int wc_stage_times(wc_handle* h, float ms[WC_NUM_STAGES]);

@@ -1,4 +1,4 @@
-"""torchrun worker for tests/test_slab_gpu.py::test_nccl_ranks_equal_whole_grid."""
+"""torchrun worker for tests/test_slab_gpu.py::test_multi_process_ranks_equal_whole_grid."""
 import os
 import sys
 
@@ -13,6 +13,7 @@ from watercube_b200 import capi, slab  # noqa: E402
 
 def main():
     out_dir, steps = sys.argv[1], int(sys.argv[2])
+    exchange = sys.argv[3] if len(sys.argv) > 3 else "nccl"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -30,8 +31,13 @@ def main():
                              stream=stream.cuda_stream)
     b.upload(parts[rank])
     drv = slab.SlabDriver(b, rank, world)
+    if exchange == "peer":
+        slab.attach_peers_ipc(b, rank, world)
     for s in range(steps):
-        slab.run_step(drv, FRAME_DT)
+        if exchange == "peer":
+            slab.run_step_peer(b, FRAME_DT)
+        else:
+            slab.run_step(drv, FRAME_DT)
         np.save(os.path.join(out_dir, f"buf1_s{s}_r{rank}.npy"), b.download(1))
     dist.barrier()
     dist.destroy_process_group()

@@ -81,6 +81,39 @@ def test_virtual_ranks_on_one_gpu_equal_whole_grid(capi, world, simple):
         dr.backend.fluid.close()
 
 
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_peer_memory_exchange_virtual_ranks_equal_whole_grid(capi, world):
+    """wc_slab_peer_attach: the phases push their messages into the neighbour's buffers and
+    signal on the device; no host-side exchange.  Same bit-exactness as the NCCL path."""
+    sc = make_scene(80000, seed=7)
+    steps = 6
+    ref = whole_grid_run(capi, sc, steps)
+    d = capi.derive(capi.default_params(num_particles=sc.n, **scene_params(sc)))
+    hist = np.bincount(slab.layer_of(sc.particles[:, 2], d.bin_size, sc.grid_res),
+                       minlength=sc.grid_res)
+    cuts = slab.slab_cuts(hist, world)
+    parts = slab.decompose(sc.particles, cuts, d.bin_size, sc.grid_res)
+    backends = []
+    for r in range(world):
+        b = slab.CudaSlabBackend(scene_params(sc), cuts[r], cuts[r + 1], capacity=sc.n,
+                                 ghost_capacity=sc.n, migrant_capacity=8192)
+        b.upload(parts[r])
+        backends.append(b)
+    slab.attach_peers_local(backends)
+    migrated = 0
+    for s in range(steps):
+        slab.run_step_peer_local(backends, FRAME_DT)
+        migrated += sum(b.info["migrants_in_below"] + b.info["migrants_in_above"] for b in backends)
+        buf2 = np.concatenate([b.download(2) for b in backends])
+        buf1 = np.concatenate([b.download(1) for b in backends])
+        np.testing.assert_array_equal(buf2, ref[s][1], err_msg=f"sorted buffer, step {s}")
+        np.testing.assert_array_equal(buf1, ref[s][0], err_msg=f"state buffer, step {s}")
+    if world > 1:
+        assert migrated > 0
+    for b in backends:
+        b.fluid.close()
+
+
 def test_slab_capacity_overflow_is_reported(capi):
     sc = make_scene(20000)
     b = slab.CudaSlabBackend(scene_params(sc), 0, sc.grid_res, capacity=sc.n, ghost_capacity=16,
@@ -99,7 +132,9 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def test_nccl_ranks_equal_whole_grid(capi, tmp_path):
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+def test_multi_process_ranks_equal_whole_grid(capi, tmp_path, exchange):
+    """One process per GPU: NCCL P2P exchange, and the CUDA-IPC peer-memory exchange."""
     import torch
 
     world = min(torch.cuda.device_count(), 4)
@@ -111,7 +146,7 @@ def test_nccl_ranks_equal_whole_grid(capi, tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port",
            str(_free_port()), os.path.join(ROOT, "tests", "slab_nccl_worker.py"), str(tmp_path),
-           str(steps)]
+           str(steps), exchange]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     for s in range(steps):

@@ -32,7 +32,8 @@ EXPORTS = (
     "wc_download_forces", "wc_upload_sorted", "wc_device_ptrs", "wc_export_aos_device", "wc_sync",
     "wc_stage_times", "wc_launch_count", "wc_slab_get_view", "wc_slab_clear_recv",
     "wc_slab_sort_count", "wc_slab_sync_info", "wc_slab_reorder", "wc_slab_density",
-    "wc_slab_update", "wc_advect_only",
+    "wc_slab_update", "wc_advect_only", "wc_slab_ipc_export", "wc_slab_peer_open",
+    "wc_slab_peer_attach",
 )
 
 
@@ -79,6 +80,10 @@ class SlabView(C.Structure):
         ("vel_pres_sorted", C.c_void_p), ("mig_bytes", C.c_uint64), ("lc_bytes", C.c_uint64),
         ("owned_first", C.c_int32), ("reserved", C.c_int32),
     ]
+
+
+class SlabIpc(C.Structure):
+    _fields_ = [("mem", (C.c_ubyte * 64) * 7), ("device", C.c_int32), ("ghost_capacity", C.c_int32)]
 
 
 SLAB_INFO = ("n_owned", "n_first", "n_last", "n_ghost_below", "n_ghost_above", "errors",
@@ -135,6 +140,9 @@ def lib():
             "wc_slab_reorder": [vp],
             "wc_slab_density": [vp, C.POINTER(StepParams)],
             "wc_slab_update": [vp, f32, C.POINTER(StepParams)],
+            "wc_slab_ipc_export": [vp, C.POINTER(SlabIpc)],
+            "wc_slab_peer_open": [vp, i32, C.POINTER(SlabIpc)],
+            "wc_slab_peer_attach": [vp, i32, vp],
         }
         for name, argtypes in sig.items():
             fn = getattr(L, name)
@@ -304,6 +312,19 @@ class Fluid:
 
     def slab_update(self, frame_dt=1.0 / 60.0):
         check(lib().wc_slab_update(self._h, float(frame_dt), C.byref(self.step_params)))
+
+    # -- peer-memory exchange (include/wc_sph.h, wc_slab_peer_*)
+    def slab_ipc_export(self) -> bytes:
+        blob = SlabIpc()
+        check(lib().wc_slab_ipc_export(self._h, C.byref(blob)))
+        return bytes(blob)
+
+    def slab_peer_open(self, direction, blob: bytes):
+        check(lib().wc_slab_peer_open(self._h, int(direction),
+                                      C.byref(SlabIpc.from_buffer_copy(blob))))
+
+    def slab_peer_attach(self, direction, other: "Fluid"):
+        check(lib().wc_slab_peer_attach(self._h, int(direction), other._h))
 
     # -- inspection
     def cells(self, neighbour_counts=False):

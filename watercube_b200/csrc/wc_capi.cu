@@ -143,7 +143,25 @@ struct wc_handle {
     unsigned long long* scan_status_x[4] = {}; // extra scan states: ghost-low, ghost-high, mig 0/1
     unsigned int* scan_counter_x[4] = {};
     size_t mig_bytes = 0, lc_bytes = 0;
+
+    // ---- peer-memory exchange (wc_slab_peer_*): the neighbours' buffers mapped into this
+    // process / context, their signal arrays, and this handle's own signal array
+    struct Peer {
+        bool on = false, ipc = false;
+        float4* pos1 = nullptr;     // neighbour's buffer 2 (sorted), incl. its ghost slots
+        float4* vel1 = nullptr;
+        float4* mig_in = nullptr;   // neighbour's mig_in[1 - d]
+        uint32_t* lc_recv = nullptr;  // neighbour's lc_recv[1 - d]
+        uint32_t* sig = nullptr;    // neighbour's signal array
+        void* ipc_base[5] = {};     // what cudaIpcCloseMemHandle needs
+        int n_owned = 0;            // neighbour's owned count of the current step
+    } peer[2];
+    uint32_t* sig = nullptr;        // [kSigPhases * 2]: raised by the neighbours
+    uint32_t step_no = 0;
+    bool peer_mode() const { return peer[0].on || peer[1].on; }
 };
+
+enum { kSigLc = 0, kSigHaloPos = 1, kSigHaloRho = 2, kSigMig = 3, kSigPhases = 4 };
 
 namespace {
 
@@ -184,6 +202,49 @@ int record(wc_handle* h, int idx) {
     return WC_OK;
 }
 
+// ---- peer-memory exchange helpers (no-ops unless wc_slab_peer_* attached a neighbour)
+// Blocks this handle's stream until both attached neighbours have raised `phase` to `value`.
+int peer_wait(wc_handle* h, int phase, uint32_t value) {
+    if (!h->peer_mode() || value == 0) return WC_OK;
+    const uint32_t* fa = h->peer[0].on ? h->sig + phase * 2 + 0 : nullptr;
+    const uint32_t* fb = h->peer[1].on ? h->sig + phase * 2 + 1 : nullptr;
+    k_wait_signals<<<1, 2, 0, h->stream>>>(fa, fb, value);
+    WC_CHECK_LAUNCH(h);
+    return WC_OK;
+}
+
+// Raises `phase` at the neighbour in direction d (it sees the signal as coming from 1 - d).
+int peer_signal(wc_handle* h, int d, int phase) {
+    k_signal<<<1, 1, 0, h->stream>>>(h->peer[d].sig + phase * 2 + (1 - d), h->step_no);
+    WC_CHECK_LAUNCH(h);
+    return WC_OK;
+}
+
+// First / last owned layer of buffer 2 -> the neighbours' ghost slots, then the signal.
+// The layer sent down becomes the lower neighbour's ghost-high slice (right after its owned
+// particles), the layer sent up the upper neighbour's ghost-low slice (right before them).
+int peer_push_halo(wc_handle* h, bool with_vel, int phase) {
+    if (!h->peer_mode()) return WC_OK;
+    int rc;
+    for (int d = 0; d < 2; d++) {
+        if (!h->peer[d].on) continue;
+        const size_t n_layer = (size_t)(d == 0 ? h->n_first : h->n_last);
+        const size_t src = (size_t)h->Cg + (d == 0 ? 0 : (size_t)(h->n - h->n_last));
+        const size_t dst = d == 0 ? (size_t)h->Cg + (size_t)h->peer[d].n_owned
+                                  : (size_t)h->Cg - n_layer;
+        if (n_layer > 0) {
+            WC_CUDA(cudaMemcpyAsync(h->peer[d].pos1 + dst, h->pos[1] + src, n_layer * sizeof(float4),
+                                    cudaMemcpyDeviceToDevice, h->stream));
+            if (with_vel)
+                WC_CUDA(cudaMemcpyAsync(h->peer[d].vel1 + dst, h->vel[1] + src,
+                                        n_layer * sizeof(float4), cudaMemcpyDeviceToDevice,
+                                        h->stream));
+        }
+        if ((rc = peer_signal(h, d, phase))) return rc;
+    }
+    return WC_OK;
+}
+
 // Sort::run part 1 (Sort.cpp:255-259): clear, count, scan.  In slab mode the input is the
 // virtual array [migrants from below | owned | migrants from above] and only the owned
 // layers are scanned (the ghost layers' offsets come from the neighbours' counts).
@@ -209,6 +270,8 @@ int sort_count_phase(wc_handle* h, bool timed) {
         return WC_OK;
     }
     const int G2 = G * G, M = h->M, n_old = h->n_in_old, total = M + n_old + M;
+    h->step_no++;
+    if ((rc = peer_wait(h, kSigMig, h->step_no - 1))) return rc;  // last step's migrants
     // received migrants -> the slots before / after the owned region of buffer 1
     k_unpack_migrants<<<div_up(M, 256), 256, 0, h->stream>>>(h->mig_in[0], M, h->pos[0], h->vel[0],
                                                            h->m_in + 0);
@@ -230,6 +293,12 @@ int sort_count_phase(wc_handle* h, bool timed) {
                                                        (uint32_t)h->Cg, h->info_dev,
                                                        h->lc_send[0], h->lc_send[1]);
     WC_CHECK_LAUNCH(h);
+    for (int d = 0; d < 2; d++) {  // peer mode: layer counts straight into the neighbours
+        if (!h->peer[d].on) continue;
+        WC_CUDA(cudaMemcpyAsync(h->peer[d].lc_recv, h->lc_send[d], h->lc_bytes,
+                                cudaMemcpyDeviceToDevice, h->stream));
+        if ((rc = peer_signal(h, d, kSigLc))) return rc;
+    }
     if (timed && (rc = record(h, 2))) return rc;
     h->info_valid = false;
     return WC_OK;
@@ -526,7 +595,7 @@ int wc_create(const wc_params* p, wc_handle** out) {
         h->m_in = (uint32_t*)((char*)h->arena + off);
         h->info_dev = h->m_in + 8;
         h->mig_bytes = (size_t)(kMigHeaderFloat4 + 2 * (size_t)h->M) * sizeof(float4);
-        h->lc_bytes = (1 + G2) * sizeof(uint32_t);
+        h->lc_bytes = (kLcHeader + G2) * sizeof(uint32_t);
         for (int k = 0; k < 2; k++) {
             WC_ALLOC(h->mig_out[k], h->mig_bytes);
             WC_ALLOC(h->mig_in[k], h->mig_bytes);
@@ -541,6 +610,8 @@ int wc_create(const wc_params* p, wc_handle** out) {
         WC_ALLOC(h->slots, 2 * (capz + 1) * sizeof(uint32_t));
         WC_ALLOC(h->errors, 256);
         cudaMemsetAsync(h->errors, 0, 256, h->stream);
+        WC_ALLOC(h->sig, 256);
+        cudaMemsetAsync(h->sig, 0, 256, h->stream);
         e = cudaMallocHost((void**)&h->info_host, 64);
         if (e != cudaSuccess) {
             wc_destroy(h);
@@ -603,6 +674,11 @@ int wc_destroy(wc_handle* h) {
     cudaFree(h->flags);
     cudaFree(h->slots);
     cudaFree(h->errors);
+    cudaFree(h->sig);
+    for (int d = 0; d < 2; d++)
+        if (h->peer[d].ipc)
+            for (void* base : h->peer[d].ipc_base)
+                if (base) cudaIpcCloseMemHandle(base);
     if (h->info_host) cudaFreeHost(h->info_host);
     for (int i = 0; i <= WC_NUM_STAGES; i++)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -851,6 +927,10 @@ int wc_slab_sync_info(wc_handle* h, int32_t info[8]) {
     if (!info) return fail(WC_ERR_INVALID, "NULL argument");
     WC_NEED_SLAB(h);
     uint32_t* hi = h->info_host;
+    int rcw = peer_wait(h, kSigLc, h->step_no);
+    if (rcw) return rcw;
+    WC_CUDA(cudaMemcpyAsync(hi + 8, h->lc_recv[0] + 1, 4, cudaMemcpyDeviceToHost, h->stream));
+    WC_CUDA(cudaMemcpyAsync(hi + 9, h->lc_recv[1] + 1, 4, cudaMemcpyDeviceToHost, h->stream));
     WC_CUDA(cudaMemcpyAsync(hi, h->info_dev, 12, cudaMemcpyDeviceToHost, h->stream));
     WC_CUDA(cudaMemcpyAsync(hi + 3, h->lc_recv[0], 4, cudaMemcpyDeviceToHost, h->stream));
     WC_CUDA(cudaMemcpyAsync(hi + 4, h->lc_recv[1], 4, cudaMemcpyDeviceToHost, h->stream));
@@ -868,6 +948,11 @@ int wc_slab_sync_info(wc_handle* h, int32_t info[8]) {
     h->n_last = (int)hi[2];
     h->n_glow = (int)hi[3];
     h->n_ghigh = (int)hi[4];
+    h->peer[0].n_owned = (int)hi[8];
+    h->peer[1].n_owned = (int)hi[9];
+    if (h->peer_mode() && (h->n_first > h->Cg || h->n_last > h->Cg))
+        return fail(WC_ERR_CAPACITY, "boundary layer of %d / %d particles exceeds the neighbours' "
+                                     "slab_ghost_capacity %d", h->n_first, h->n_last, h->Cg);
     h->info_valid = true;
     return WC_OK;
 }
@@ -891,7 +976,9 @@ int wc_slab_reorder(wc_handle* h) {
     WC_CHECK_LAUNCH(h);
     // the virtual input still has the OLD owned count between the migrant slots
     const int n_in = h->M + h->n_in_old + h->M;
-    return sort_reorder_phase(h, true, n_in, h->n);
+    int rc = sort_reorder_phase(h, true, n_in, h->n);
+    if (rc) return rc;
+    return peer_push_halo(h, false, kSigHaloPos);  // peer mode: halo positions
 }
 
 int wc_slab_density(wc_handle* h, const wc_step_params* sp) {
@@ -899,7 +986,9 @@ int wc_slab_density(wc_handle* h, const wc_step_params* sp) {
     int rc = check_step_params(sp);
     if (rc) return rc;
     if (!h->sorted_valid) return fail(WC_ERR_INVALID, "wc_slab_density needs wc_slab_reorder");
+    if ((rc = peer_wait(h, kSigHaloPos, h->step_no))) return rc;
     if ((rc = run_density(h, *sp))) return rc;
+    if ((rc = peer_push_halo(h, true, kSigHaloRho))) return rc;  // now carrying rho, P and v
     return record(h, 4);
 }
 
@@ -911,6 +1000,7 @@ int wc_slab_update(wc_handle* h, float frame_dt, const wc_step_params* sp) {
     const float bin = h->d.bin_size;
     if (!(50.0f * fabsf(frame_dt * h->p.time_scale) < bin))
         return fail(WC_ERR_INVALID, "dt too large for one-layer migration: 50 * dt >= binSize");
+    if ((rc = peer_wait(h, kSigHaloRho, h->step_no))) return rc;
     if ((rc = run_update(h, *sp, frame_dt))) return rc;
     // Particles whose new z-layer left the slab: only the first / last owned layer can lose
     // any (|v| dt < binSize), and those layers are the head / tail of the sorted order.
@@ -936,10 +1026,95 @@ int wc_slab_update(wc_handle* h, float frame_dt, const wc_step_params* sp) {
             own_pos + start, own_vel + start, n_layer, flags, slots, h->M, h->mig_out[dir],
             h->errors);
         WC_CHECK_LAUNCH(h);
+        if (h->peer[dir].on) {  // peer mode: the message goes straight into the neighbour
+            WC_CUDA(cudaMemcpyAsync(h->peer[dir].mig_in, h->mig_out[dir], h->mig_bytes,
+                                    cudaMemcpyDeviceToDevice, h->stream));
+            if ((rc = peer_signal(h, dir, kSigMig))) return rc;
+        }
     }
     h->n_in_old = h->n;
     if ((rc = record(h, 5))) return rc;
     h->have_times = (h->p.flags & WC_FLAG_STAGE_TIMING) != 0;
+    return WC_OK;
+}
+
+int wc_slab_ipc_export(wc_handle* h, wc_slab_ipc* out) {
+    if (!out) return fail(WC_ERR_INVALID, "NULL argument");
+    WC_NEED_SLAB(h);
+    static_assert(sizeof(cudaIpcMemHandle_t) == WC_IPC_HANDLE_BYTES, "IPC handle size");
+    void* ptrs[7] = {h->pos[1], h->vel[1], h->mig_in[0], h->mig_in[1],
+                     h->lc_recv[0], h->lc_recv[1], h->sig};
+    for (int k = 0; k < 7; k++) {
+        cudaIpcMemHandle_t mh;
+        WC_CUDA(cudaIpcGetMemHandle(&mh, ptrs[k]));
+        std::memcpy(out->mem[k], &mh, sizeof(mh));
+    }
+    out->device = h->p.device;
+    out->ghost_capacity = h->Cg;
+    return WC_OK;
+}
+
+static int peer_check(wc_handle* h, int32_t direction) {
+    if (direction != 0 && direction != 1) return fail(WC_ERR_INVALID, "direction must be 0 or 1");
+    if (h->peer[direction].on) return fail(WC_ERR_INVALID, "neighbour %d is already attached", direction);
+    if (h->step_no != 0) return fail(WC_ERR_INVALID, "attach neighbours before the first step");
+    return WC_OK;
+}
+
+int wc_slab_peer_open(wc_handle* h, int32_t direction, const wc_slab_ipc* peer) {
+    if (!peer) return fail(WC_ERR_INVALID, "NULL argument");
+    WC_NEED_SLAB(h);
+    int rc = peer_check(h, direction);
+    if (rc) return rc;
+    if (peer->ghost_capacity != h->Cg)
+        return fail(WC_ERR_INVALID, "neighbour has another slab_ghost_capacity (%d vs %d)",
+                    peer->ghost_capacity, h->Cg);
+    wc_handle::Peer& P = h->peer[direction];
+    // what this rank writes at the neighbour: its sorted buffers, the message buffers that
+    // face this rank (index 1 - direction), its signals
+    const int want[5] = {0, 1, 2 + (1 - direction), 4 + (1 - direction), 6};
+    void* mapped[5] = {};
+    for (int k = 0; k < 5; k++) {
+        cudaIpcMemHandle_t mh;
+        std::memcpy(&mh, peer->mem[want[k]], sizeof(mh));
+        cudaError_t e = cudaIpcOpenMemHandle(&mapped[k], mh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < k; q++) cudaIpcCloseMemHandle(mapped[q]);
+            return fail(WC_ERR_CUDA, "cudaIpcOpenMemHandle (neighbour %d, buffer %d): %s", direction,
+                        want[k], cudaGetErrorString(e));
+        }
+        P.ipc_base[k] = mapped[k];
+    }
+    P.pos1 = (float4*)mapped[0];
+    P.vel1 = (float4*)mapped[1];
+    P.mig_in = (float4*)mapped[2];
+    P.lc_recv = (uint32_t*)mapped[3];
+    P.sig = (uint32_t*)mapped[4];
+    P.ipc = true;
+    P.on = true;
+    return WC_OK;
+}
+
+int wc_slab_peer_attach(wc_handle* h, int32_t direction, wc_handle* peer) {
+    if (!peer) return fail(WC_ERR_INVALID, "NULL argument");
+    WC_NEED_SLAB(h);
+    if (!peer->slab) return fail(WC_ERR_INVALID, "the neighbour is not a slab handle");
+    int rc = peer_check(h, direction);
+    if (rc) return rc;
+    if (peer->Cg != h->Cg) return fail(WC_ERR_INVALID, "neighbour has another slab_ghost_capacity");
+    if (peer->p.device != h->p.device) {  // same process, other device: plain peer access
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer->p.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            return fail(WC_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    wc_handle::Peer& P = h->peer[direction];
+    P.pos1 = peer->pos[1];
+    P.vel1 = peer->vel[1];
+    P.mig_in = peer->mig_in[1 - direction];
+    P.lc_recv = peer->lc_recv[1 - direction];
+    P.sig = peer->sig;
+    P.on = true;
     return WC_OK;
 }
 

@@ -19,6 +19,7 @@
 namespace wc {
 
 constexpr int kMigHeaderFloat4 = 2;  // 32-byte message header: [count, 7 x pad]
+constexpr int kLcHeader = 2;         // layer-count message header: [n_layer, n_owned]
 
 // Incoming migrant message (header + AoS payload) -> SoA slots of buffer 1.
 __global__ void k_unpack_migrants(const float4* __restrict__ msg, int cap,
@@ -71,7 +72,7 @@ k_hash_count_slab(const float4* __restrict__ pos, int total, int M, int n_old,
 }
 
 // After the owned-layer scan: counts of the slab and its boundary layers, and the
-// layer-count messages [n_layer, counts of the layer's G*G cells] for the two neighbours.
+// layer-count messages [n_layer, n_owned, counts of the layer's G*G cells] for the neighbours.
 __global__ void k_slab_info(const uint32_t* __restrict__ counts,
                             const uint32_t* __restrict__ offsets, int G2, int Lz, uint32_t Cg,
                             uint32_t* __restrict__ info, uint32_t* __restrict__ lc_down,
@@ -82,12 +83,12 @@ __global__ void k_slab_info(const uint32_t* __restrict__ counts,
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         info[0] = n_own, info[1] = n_first, info[2] = n_last;
-        lc_down[0] = n_first;
-        lc_up[0] = n_last;
+        lc_down[0] = n_first, lc_down[1] = n_own;
+        lc_up[0] = n_last, lc_up[1] = n_own;
     }
     if (i < G2) {
-        lc_down[1 + i] = counts[(size_t)G2 + i];
-        lc_up[1 + i] = counts[(size_t)(Lz - 2) * G2 + i];
+        lc_down[kLcHeader + i] = counts[(size_t)G2 + i];
+        lc_up[kLcHeader + i] = counts[(size_t)(Lz - 2) * G2 + i];
     }
 }
 
@@ -97,8 +98,8 @@ __global__ void k_install_ghost_counts(const uint32_t* __restrict__ lc_below,
                                        uint32_t* __restrict__ counts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G2) return;
-    counts[i] = lc_below[1 + i];
-    counts[(size_t)(Lz - 1) * G2 + i] = lc_above[1 + i];
+    counts[i] = lc_below[kLcHeader + i];
+    counts[(size_t)(Lz - 1) * G2 + i] = lc_above[kLcHeader + i];
 }
 
 // End of step: particles of the first / last owned layer whose new z-layer left the slab.
@@ -130,5 +131,27 @@ __global__ void k_pack_migrants(const float4* __restrict__ pos, const float4* __
 }
 
 __global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
+
+// ---- peer-memory exchange (wc_slab_peer_*): put-with-signal over NVLink -----------------------
+// The sender copies its data into the neighbour's buffers (mapped peer memory) on its own
+// stream and then raises a monotonic step counter in the neighbour's signal array; the
+// neighbour's stream holds a one-thread kernel that spins on its local counter before the
+// consumer kernels run.  No host round trip, no collective library on the data path.
+__global__ void k_signal(uint32_t* peer_flag, uint32_t value) {
+    __threadfence_system();  // the stream-ordered copies before this kernel are complete
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flag), "r"(value) : "memory");
+}
+
+__global__ void k_wait_signals(const uint32_t* flag_a, const uint32_t* flag_b, uint32_t value) {
+    const uint32_t* f = threadIdx.x == 0 ? flag_a : flag_b;
+    if (f) {
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v < value) __nanosleep(200);
+        } while (v < value);
+    }
+    __threadfence_system();
+}
 
 }  // namespace wc

@@ -128,6 +128,61 @@ def run_step(driver: SlabDriver, frame_dt: float, group=None):
                 req.wait()
 
 
+# --------------------------------------------------------------------------- peer-memory mode
+# With the neighbours attached (CudaSlabBackend.attach_peers_*), the native phases move the
+# four messages themselves -- copies into the neighbour's mapped buffers plus device-side
+# signals (include/wc_sph.h, wc_slab_peer_*) -- so a step is just the five phase calls.
+def attach_peers_ipc(backend, rank: int, world: int, group=None):
+    """One process per GPU: trade the IPC blobs over torch.distributed, open the neighbours."""
+    import torch.distributed as dist
+
+    blobs = [None] * world
+    dist.all_gather_object(blobs, backend.fluid.slab_ipc_export(), group=group)
+    for d, peer in ((0, rank - 1), (1, rank + 1)):
+        if 0 <= peer < world:
+            backend.fluid.slab_peer_open(d, blobs[peer])
+        else:
+            backend.clear_recv(d)
+    dist.barrier(group=group)
+
+
+def attach_peers_local(backends: Sequence["CudaSlabBackend"]):
+    """Several slab handles in this process (virtual ranks, or one process driving many GPUs)."""
+    for r, b in enumerate(backends):
+        for d, peer in ((0, r - 1), (1, r + 1)):
+            if 0 <= peer < len(backends):
+                b.fluid.slab_peer_attach(d, backends[peer].fluid)
+            else:
+                b.clear_recv(d)
+
+
+def run_step_peer(backend, frame_dt: float):
+    """One step of one rank in peer-memory mode (every rank runs this; no host exchange)."""
+    backend.sort_count()
+    info = backend.sync_info()
+    if info["errors"]:
+        raise RuntimeError(f"slab capacity overflow / lost migrants: {info}")
+    backend.reorder()
+    backend.density()
+    backend.update(frame_dt)
+
+
+def run_step_peer_local(backends: Sequence["CudaSlabBackend"], frame_dt: float):
+    """Virtual ranks of one process in peer-memory mode: phase by phase over all ranks, so every
+    push a wait depends on has been queued before the host blocks in sync_info."""
+    for b in backends:
+        b.sort_count()
+    for b in backends:
+        if b.sync_info()["errors"]:
+            raise RuntimeError(f"slab capacity overflow / lost migrants: {b.info}")
+    for b in backends:
+        b.reorder()
+    for b in backends:
+        b.density()
+    for b in backends:
+        b.update(frame_dt)
+
+
 def run_step_local(drivers: Sequence[SlabDriver], frame_dt: float):
     """One step of several virtual ranks living in this process (lock-step, copies instead of
     messages).  Used to test the decomposition on a single GPU."""

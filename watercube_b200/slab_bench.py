@@ -91,6 +91,15 @@ def run(args, rank, world, local):
                              flags=flags, stream=stream.cuda_stream)
     b.upload(mine)
     drv = slab.SlabDriver(b, rank, world)
+    peer = args.exchange == "peer"
+    if peer:
+        slab.attach_peers_ipc(b, rank, world)
+
+    def one_step():
+        if peer:
+            slab.run_step_peer(b, FRAME_DT)
+        else:
+            slab.run_step(drv, FRAME_DT)
 
     def barrier():
         dist.barrier()
@@ -98,7 +107,7 @@ def run(args, rank, world, local):
 
     warmup = max(args.warmup, 3)
     for _ in range(warmup):
-        slab.run_step(drv, FRAME_DT)
+        one_step()
     barrier()
 
     sampler = bench.ClockSampler(local)
@@ -112,7 +121,7 @@ def run(args, rank, world, local):
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        slab.run_step(drv, FRAME_DT)
+        one_step()
         for k, v in b.fluid.stage_times().items():
             stage_ms[k] += v
     e1.record(stream)
@@ -144,7 +153,7 @@ def run(args, rank, world, local):
         for _ in range(steps_e):
             b.fluid.upload((h_in.data_ptr(), n_cur))
             h2d += n_cur * 32
-            slab.run_step(drv, FRAME_DT)
+            one_step()
             n_cur = b.num_particles
             b.fluid.download(1, out=(h_out.data_ptr(), n_cur))
             d2h += n_cur * 32
@@ -185,7 +194,9 @@ def run(args, rank, world, local):
             "config": bench.workload_config(args, _Sc, n_total, world, {
                 "l2": "per-rank working set > L2, no flush", "kernels": "tiled",
                 "slab_cuts": [int(c) for c in cuts], "particles_per_rank": counts,
-                "exchange": "NCCL P2P with slab neighbours: layer counts, halo positions, "
+                "exchange": ("peer memory (CUDA IPC over NVLink): copies into the neighbour's "
+                             "buffers + device-side signals" if peer else "NCCL P2P") +
+                            " with slab neighbours: layer counts, halo positions, "
                             "halo rho/P/velocity, migrants"}),
             "stage_ms": per_stage,
             "roofline": {"bound": "hbm", "kernel": bench.KERNEL_NAMES[dom], "achieved": achieved,
