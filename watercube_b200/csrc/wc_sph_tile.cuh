@@ -48,6 +48,14 @@ constexpr int kDensityWarps = WC_DENSITY_WARPS;  // warps (= groups) per block, 
 #ifndef WC_UPDATE_MIN_BLOCKS
 #define WC_UPDATE_MIN_BLOCKS 8
 #endif
+// 1: the replay keeps WC_REPLAY_WORDS list words resident as a sliding ring (lanes run ahead of
+// the slowest lane by up to the ring); 0 (default): hard batches of WC_REPLAY_WORDS words.  The
+// ring cuts the pair-loop iterations by a third but measured 4-15 % SLOWER on B200
+// (profiles/r01_variant_sweep.md): the pass is bound by shared-memory wavefronts of the
+// per-lane candidate loads, which the ring does not reduce.  Kept for the record / re-tuning.
+#ifndef WC_WALK_RING
+#define WC_WALK_RING 0
+#endif
 constexpr int kUpdateWarps = WC_UPDATE_WARPS;  // warps per block, update pass (6 KB stage each)
 constexpr int kChunk = 128;                // staged candidates per density batch (4 words)
 constexpr int kCullDepth = 4;              // density pass: cull loads in flight per lane
@@ -380,6 +388,124 @@ struct UpdateAcc {
 };
 
 // ---------------------------------------------------------------------------------------
+// Ring replay of a group's neighbour list (update pass).  With hard batches every lane waits at
+// each batch's end for the lane with the most accepted bits in that batch (tools/model_walk.py:
+// 41 pair-loop iterations per group at 5 words against 25 for the whole list at once).  Here
+// the stage holds the R = kReplayWords most recent list words as a ring: a lane drains its own
+// bits word after word and may run ahead of the slowest lane by the resident window; once every
+// lane has left the oldest word its slot is refilled with the next list word (candidate gathers
+// issued before the iteration's pair math, stored after it).  Same pairs, same per-lane order
+// as the batched walk, so the sums are bit-identical to it.
+__device__ __forceinline__ void replay_ring(UpdateStage& st, UpdateAcc& acc,
+                                            const uint32_t* __restrict__ widx,
+                                            const uint32_t* __restrict__ wmask, int nw,
+                                            uint32_t first_target,
+                                            const float4* __restrict__ pos_rho,
+                                            const float4* __restrict__ vel_pres,
+                                            const SphConsts& c, float4 p, float4 v) {
+    constexpr int R = kReplayWords;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    {   // fill the ring with words [0, min(R, nw))
+        uint32_t jj[R];
+#pragma unroll
+        for (int u = 0; u < R; u++) {
+            jj[u] = kNoIndex;
+            uint32_t mk = 0u;
+            if (u < nw) {
+                jj[u] = widx[(size_t)u * 32];
+                mk = wmask[(size_t)u * 32];
+            }
+            st.mask[u * 32 + lane] = mk;
+        }
+#pragma unroll
+        for (int u = 0; u < R; u++) {
+            if (jj[u] != kNoIndex) {
+                float4 qa = pos_rho[jj[u]];
+                qa.w = __frcp_rn(qa.w);
+                st.a[u * 32 + lane] = qa;
+                st.b[u * 32 + lane] = vel_pres[jj[u]];
+            }
+        }
+        __syncwarp();
+        // a listed candidate that is one of this group's own targets: drop that target's self
+        // pair (it would add exactly zero; this only saves the evaluation)
+#pragma unroll
+        for (int u = 0; u < R; u++) {
+            const uint32_t t = jj[u] - first_target;
+            if (t < 32u) atomicAnd(&st.mask[u * 32 + t], ~(1u << lane));
+        }
+        __syncwarp();
+    }
+    // warp-uniform ring state: resident words are [base, horizon), word w sits in slot w % R
+    int base = 0, bslot = 0, horizon = min(nw, R);
+    uint32_t jn = kNoIndex, mkn = 0u;  // index / mask word of the next refill, prefetched
+    if (R < nw) {
+        jn = widx[(size_t)R * 32];
+        mkn = wmask[(size_t)R * 32];
+    }
+    // per-lane walk state
+    int wl = 0, slot = 0;              // the word this lane is draining, and its slot
+    unsigned m = st.mask[lane];
+    float4 qa0 = make_float4(0, 0, 0, 0), qb0 = qa0, qa1 = qa0, qb1 = qa0;
+    auto pick = [&](float4& qa, float4& qb) -> bool {
+        if (m == 0u && wl + 1 < horizon) {
+            wl++;
+            slot = (slot + 1 == R) ? 0 : slot + 1;
+            m = st.mask[slot * 32 + lane];
+        }
+        const bool on = m != 0u;
+        const int lz = __clz((int)m);  // 32 when no bit is left
+        if (on) {
+            const float4* q = st.a + slot * 32 + (31 - lz);
+            qa = q[0];
+            qb = q[kReplaySlots];
+        }
+        m &= ~(0x80000000u >> (lz & 31));
+        return on;
+    };
+    for (;;) {
+        // the oldest word any lane still needs
+        const int wmin = __reduce_min_sync(full, (m != 0u) ? wl : wl + 1);
+        if (wmin >= nw) break;
+        const bool retire = base < wmin;            // every lane has left word `base`
+        const bool refill = retire && base + R < nw;
+        float4 qan = make_float4(0, 0, 0, 0), qbn = qan;
+        if (refill && jn != kNoIndex) {
+            qan = pos_rho[jn];
+            qbn = vel_pres[jn];
+        }
+        const bool on0 = pick(qa0, qb0);
+        const bool on1 = pick(qa1, qb1);
+        acc.pair(c, p, v, qa0, qb0, on0);
+        acc.pair(c, p, v, qa1, qb1, on1);
+        if (retire) {
+            if (refill) {
+                st.mask[bslot * 32 + lane] = mkn;
+                if (jn != kNoIndex) {
+                    qan.w = __frcp_rn(qan.w);
+                    st.a[bslot * 32 + lane] = qan;
+                    st.b[bslot * 32 + lane] = qbn;
+                }
+                __syncwarp();
+                const uint32_t t = jn - first_target;
+                if (t < 32u) atomicAnd(&st.mask[bslot * 32 + t], ~(1u << lane));
+                __syncwarp();
+                const int wn = base + R + 1;
+                jn = kNoIndex, mkn = 0u;
+                if (wn < nw) {
+                    jn = widx[(size_t)wn * 32];
+                    mkn = wmask[(size_t)wn * 32];
+                }
+            }
+            base++;
+            bslot = (bslot + 1 == R) ? 0 : bslot + 1;
+            horizon = min(nw, base + R);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // The shared gather driver: phase 1 (cull + stage) and the hand-over to acc.process().
 struct GroupGeom {
     int x0, x1;        // cell columns of the nine slices
@@ -568,6 +694,10 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
         const uint32_t* widx = list.idx + (size_t)x.g * list.cap_words * 32 + lane;
         const uint32_t* wmask = list.mask + (size_t)x.g * list.cap_words * 32 + lane;
         const uint32_t first_target = (uint32_t)(x.i - lane);
+#if WC_WALK_RING
+        replay_ring(st, acc, widx, wmask, (int)nw, first_target, pos_rho, vel_pres, c, p, v);
+    }
+#else
         st.init(lane);
         for (uint32_t w0 = 0; w0 < nw; w0 += kReplayWords) {
             uint32_t jj[kReplayWords];
@@ -603,6 +733,7 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
             __syncwarp();
         }
     }
+#endif
     if (!x.valid) return;
     const float kp = -0.5f * (c.m * c.spikyC), kv = c.m * c.viscC;
     float4 po, vo, fo;
