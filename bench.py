@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--simple-kernels", action="store_true")
+    ap.add_argument("--e2e-separate-calls", action="store_true",
+                    help="e2e through upload + step + download instead of wc_step_host")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: slab-neighbour transport (peer memory over NVLink, or NCCL P2P)")
     return ap.parse_args()
@@ -313,9 +315,14 @@ def run_b200(args):
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            fl.upload((h_in.data_ptr(), n))
-            fl.step(FRAME_DT)
-            fl.download(1, out=(h_out.data_ptr(), n))   # syncs: the result is on the host
+            if args.e2e_separate_calls:
+                fl.upload((h_in.data_ptr(), n))
+                fl.step(FRAME_DT)
+                fl.download(1, out=(h_out.data_ptr(), n))   # syncs: the result is on the host
+            else:
+                # wc_step_host: H2D of the pinned input, the step, and the result stored into
+                # the pinned output by the update kernel itself; returns with it complete
+                fl.step_host((h_in.data_ptr(), n), h_out.data_ptr(), FRAME_DT)
             e1.record(stream)
             e1.synchronize()
             if it >= 3:
@@ -323,7 +330,10 @@ def run_b200(args):
             h_in, h_out = h_out, h_in
         e2e_ms = float(np.mean(ev))
         e2e = {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32}
+               "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32,
+               "api": "wc_upload_particles + wc_step + wc_download_particles"
+                      if args.e2e_separate_calls else
+                      "wc_step_host (pinned host AoS in and out; D2H fused into the update kernel)"}
         launches_e2e = 3  # aos->soa, soa->aos + the step's kernels (reported for context)
     clocks = sampler.stop(t_wall0, t_wall1)
 

@@ -153,6 +153,16 @@ int wc_download_particles(wc_handle* h, int32_t which, wc_particle* host_aos);
 /* Fluid::update(double time) (Fluid.cpp:342-354): sort(buf1->buf2); density(buf2);
  * update(buf2->buf1, dt = frame_dt * time_scale).  Asynchronous on the handle's stream. */
 int wc_step(wc_handle* h, float frame_dt, const wc_step_params* sp);
+/* The same step with HOST particle buffers on both sides, for callers that keep the state on
+ * the host (util::setParticles -> Fluid::update -> util::getParticles, util.cpp:42-63, as one
+ * call): uploads n particles from host_in (NULL: step the resident state), steps, and leaves
+ * the new buffer 1 in host_out (n * 32 bytes, cell-sorted order like wc_download_particles(1)).
+ * When host_out is page-locked (cudaHostAlloc / cudaHostRegister) the update kernel stores
+ * each result straight into it over PCIe, so the device-to-host copy overlaps the kernel
+ * instead of following it; pageable memory takes the copy path.  Synchronous: host_out is
+ * complete on return. */
+int wc_step_host(wc_handle* h, float frame_dt, const wc_step_params* sp,
+                 const wc_particle* host_in, int32_t n, wc_particle* host_out);
 /* Stage-level entry points, like the reference's separate runXProg methods. */
 int wc_sort_only(wc_handle* h);                                      /* Sort::run, Sort.cpp:254 */
 int wc_density_only(wc_handle* h, const wc_step_params* sp);         /* Fluid.cpp:268 */

@@ -245,6 +245,35 @@ def test_step_equals_stage_composition_and_is_deterministic(capi):
         np.testing.assert_array_equal(a, b)
 
 
+@pytest.mark.parametrize("simple", [False, True], ids=["tiled", "simple"])
+@pytest.mark.parametrize("pinned", [True, False], ids=["pinned", "pageable"])
+def test_step_host_equals_upload_step_download(capi, pinned, simple):
+    """wc_step_host (host buffers in and out; with page-locked output the update kernel stores
+    the AoS records into it directly) is bit-identical to the three separate calls, also when
+    chained and when the input is the resident state."""
+    import torch
+
+    sc = scenes.dam_break(60000, seed=17)
+    flags = capi.FLAG_SIMPLE_KERNELS if simple else 0
+    with gpu_fluid(capi, sc, flags) as fl:
+        fl.upload(sc.particles)
+        ref = []
+        for _ in range(3):
+            fl.step(FRAME_DT)
+            ref.append(fl.download(1).copy())
+    a = torch.empty((sc.n, 8), dtype=torch.float32, pin_memory=pinned)
+    b = torch.full((sc.n, 8), float("nan"), dtype=torch.float32, pin_memory=pinned)
+    a.copy_(torch.from_numpy(np.ascontiguousarray(sc.particles).view(np.float32).reshape(sc.n, 8)))
+    with gpu_fluid(capi, sc, flags) as fl:
+        fl.step_host((a.data_ptr(), sc.n), b.data_ptr(), FRAME_DT)      # host -> host
+        np.testing.assert_array_equal(b.numpy(), ref[0])
+        fl.step_host((b.data_ptr(), sc.n), a.data_ptr(), FRAME_DT)      # chained, buffers swapped
+        np.testing.assert_array_equal(a.numpy(), ref[1])
+        np.testing.assert_array_equal(fl.download(1), ref[1])           # device state agrees
+        fl.step_host(None, b.data_ptr(), FRAME_DT)                      # resident state
+        np.testing.assert_array_equal(b.numpy(), ref[2])
+
+
 def test_simple_and_tiled_kernels_agree_bitwise_on_integers(capi):
     sc = scenes.dam_break(120000, seed=13)
     res = [run_gpu_stages(capi, sc, simple) for simple in (False, True)]

@@ -28,7 +28,7 @@ PARTICLE_DTYPE = np.dtype(
 EXPORTS = (
     "wc_abi_version", "wc_last_error", "wc_default_params", "wc_default_step_params", "wc_derive",
     "wc_create", "wc_destroy", "wc_get_derived", "wc_upload_particles", "wc_download_particles",
-    "wc_step", "wc_sort_only", "wc_density_only", "wc_update_only", "wc_download_cells",
+    "wc_step", "wc_step_host", "wc_sort_only", "wc_density_only", "wc_update_only", "wc_download_cells",
     "wc_download_forces", "wc_upload_sorted", "wc_device_ptrs", "wc_export_aos_device", "wc_sync",
     "wc_stage_times", "wc_launch_count", "wc_slab_get_view", "wc_slab_clear_recv",
     "wc_slab_sort_count", "wc_slab_sync_info", "wc_slab_reorder", "wc_slab_density",
@@ -121,6 +121,7 @@ def lib():
             "wc_upload_particles": [vp, vp, i32],
             "wc_download_particles": [vp, i32, vp],
             "wc_step": [vp, f32, C.POINTER(StepParams)],
+            "wc_step_host": [vp, f32, C.POINTER(StepParams), vp, C.c_int32, vp],
             "wc_sort_only": [vp],
             "wc_density_only": [vp, C.POINTER(StepParams)],
             "wc_update_only": [vp, f32, C.POINTER(StepParams)],
@@ -270,6 +271,14 @@ class Fluid:
         check(lib().wc_step(self._h, float(frame_dt), C.byref(self.step_params)))
 
     update = step
+
+    def step_host(self, host_in, host_out, frame_dt=1.0 / 60.0):
+        """setParticles -> Fluid::update -> getParticles as one call (wc_step_host).
+        host_in: (pointer, n) or None (step the resident state); host_out: raw pointer to
+        n * 32 bytes -- page-locked memory takes the fused device-to-host path."""
+        ptr, n = host_in if host_in is not None else (None, 0)
+        check(lib().wc_step_host(self._h, float(frame_dt), C.byref(self.step_params),
+                                 C.c_void_p(ptr), int(n), C.c_void_p(host_out)))
 
     def sort_only(self):
         check(lib().wc_sort_only(self._h))

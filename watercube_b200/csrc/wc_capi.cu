@@ -363,7 +363,8 @@ int run_density(wc_handle* h, const wc_step_params& sp) {
     return WC_OK;
 }
 
-int run_update(wc_handle* h, const wc_step_params& sp, float frame_dt) {
+int run_update(wc_handle* h, const wc_step_params& sp, float frame_dt,
+               float4* aos_out = nullptr) {
     if (h->n == 0) return WC_OK;
     const SphConsts c = make_consts(h, sp, frame_dt);
     const bool dbg = h->p.flags & WC_FLAG_DEBUG_OUTPUTS;
@@ -374,7 +375,7 @@ int run_update(wc_handle* h, const wc_step_params& sp, float frame_dt) {
     const bool simple = h->p.flags & WC_FLAG_SIMPLE_KERNELS;
     if (!simple)
         launch_update_tile(h->pos[1], h->vel[1], h->offsets, c, group_table(h), h->pos[0] + h->M,
-                           h->vel[0] + h->M, dbg ? h->forces : nullptr, list, h->stream);
+                           h->vel[0] + h->M, dbg ? h->forces : nullptr, list, h->stream, aos_out);
     if (simple) {
         if (dbg)
             k_update_v1<true><<<div_up(h->n, 128), 128, 0, h->stream>>>(
@@ -759,6 +760,35 @@ int wc_step(wc_handle* h, float frame_dt, const wc_step_params* sp) {
     if ((rc = run_update(h, *sp, frame_dt))) return rc;  // Fluid.cpp:350
     if ((rc = record(h, 5))) return rc;
     h->have_times = (h->p.flags & WC_FLAG_STAGE_TIMING) != 0;
+    return WC_OK;
+}
+
+int wc_step_host(wc_handle* h, float frame_dt, const wc_step_params* sp,
+                 const wc_particle* host_in, int32_t n, wc_particle* host_out) {
+    if (!h) return fail(WC_ERR_INVALID, "handle is NULL");
+    int rc = check_step_params(sp);
+    if (rc) return rc;
+    if (h->slab) return fail(WC_ERR_INVALID, "slab handle: use the wc_slab_* sequence");
+    if (host_in && (rc = wc_upload_particles(h, host_in, n))) return rc;
+    if (!host_out && h->n > 0) return fail(WC_ERR_INVALID, "host_out is NULL");
+    WC_CUDA(cudaSetDevice(h->p.device));
+    // Page-locked destination: the update kernel writes the AoS records into it directly.
+    float4* mapped = nullptr;
+    if (h->n > 0 && !(h->p.flags & WC_FLAG_SIMPLE_KERNELS)) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, host_out) == cudaSuccess &&
+            attr.type == cudaMemoryTypeHost && attr.devicePointer)
+            mapped = static_cast<float4*>(attr.devicePointer);
+        cudaGetLastError();  // an unregistered pointer is not an error here
+    }
+    if ((rc = run_sort(h, true))) return rc;
+    if ((rc = run_density(h, *sp))) return rc;
+    if ((rc = record(h, 4))) return rc;
+    if ((rc = run_update(h, *sp, frame_dt, mapped))) return rc;
+    if ((rc = record(h, 5))) return rc;
+    h->have_times = (h->p.flags & WC_FLAG_STAGE_TIMING) != 0;
+    if (!mapped) return wc_download_particles(h, 1, host_out);
+    WC_CUDA(cudaStreamSynchronize(h->stream));
     return WC_OK;
 }
 

@@ -675,7 +675,7 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
               const uint32_t* __restrict__ offsets, SphConsts c,
               const uint4* __restrict__ groups, const uint32_t* __restrict__ num_groups,
               float4* __restrict__ pos_out, float4* __restrict__ vel_out,
-              float4* __restrict__ forces, NbrList list) {
+              float4* __restrict__ forces, NbrList list, float4* __restrict__ aos_out) {
     extern __shared__ __align__(16) unsigned char s_dyn[];  // kUpdateWarps stages (may exceed 48 KB)
     UpdateStage* s_stage = reinterpret_cast<UpdateStage*>(s_dyn);
     const int lane = threadIdx.x & 31;
@@ -742,6 +742,14 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
     pos_out[x.t] = po;
     vel_out[x.t] = vo;
     if (kDebug) forces[x.t] = fo;
+    // wc_step_host: the same record also goes out as the reference's 32-byte AoS Particle
+    // (util.h:29-35), straight into the caller's mapped pinned host buffer -- the
+    // device-to-host copy rides on the kernel instead of following it (a warp writes 1 KB
+    // contiguous).
+    if (aos_out) {
+        __stcs(&aos_out[2 * (size_t)x.t], po);
+        __stcs(&aos_out[2 * (size_t)x.t + 1], vo);
+    }
 }
 
 struct GroupTable {
@@ -767,7 +775,7 @@ inline void launch_density_tile(float4* pos_rho, float4* vel_pres, const uint32_
 inline void launch_update_tile(const float4* pos_rho, const float4* vel_pres,
                                const uint32_t* offsets, const SphConsts& c, const GroupTable& gt,
                                float4* pos_out, float4* vel_out, float4* forces, NbrList list,
-                               cudaStream_t stream) {
+                               cudaStream_t stream, float4* aos_out = nullptr) {
     const int blocks = blocks_for(gt.max_groups, kUpdateWarps);
     constexpr size_t smem = kUpdateWarps * sizeof(UpdateStage);
     if (smem > 48 * 1024) {  // opt-in size; the attribute is per device, so set it per launch
@@ -779,11 +787,11 @@ inline void launch_update_tile(const float4* pos_rho, const float4* vel_pres,
     if (forces)
         k_update_tile<true><<<blocks, kUpdateWarps * 32, smem, stream>>>(
             pos_rho, vel_pres, offsets, c, gt.groups, gt.count, pos_out, vel_out, forces,
-            list);
+            list, aos_out);
     else
         k_update_tile<false><<<blocks, kUpdateWarps * 32, smem, stream>>>(
             pos_rho, vel_pres, offsets, c, gt.groups, gt.count, pos_out, vel_out, nullptr,
-            list);
+            list, aos_out);
 }
 
 }  // namespace wc
