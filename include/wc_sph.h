@@ -254,6 +254,36 @@ int wc_slab_ipc_export(wc_handle* h, wc_slab_ipc* out);
 int wc_slab_peer_open(wc_handle* h, int32_t direction, const wc_slab_ipc* peer);
 int wc_slab_peer_attach(wc_handle* h, int32_t direction, wc_handle* peer);
 
+/* ---- inspection ----------------------------------------------------------
+ * The reference verifies itself by eye: render modes 1-4 colour a particle red when it left
+ * the box or its density is not positive (assets/fluid/particle.vert:35-55), and
+ * Sort::printGrids (Sort.cpp:237-249) / util::printParticles (util.cpp:113-126) dump tables
+ * to the debug console.  wc_diagnose reduces buffer `which` (1 = current state, 2 = sorted
+ * input of the last step) on the device -- one pass over 32 bytes per particle, fp64 sums
+ * folded in a fixed order (same buffer -> same bits) -- and syncs.  Sums cover the VALID
+ * particles only.  Works on slab handles too (the owned particles; cell fields are -1). */
+#define WC_DIAG_HIST_BINS 32
+#define WC_DIAG_HIST_PER_UNIT 4 /* histogram bins per unit of density / rest_density */
+typedef struct wc_diagnostics {
+    int64_t particles;       /* particles looked at */
+    int64_t invalid;         /* outside [0,size]^3, non-finite state, or density <= 0 */
+    int64_t out_of_box;      /* the position part of `invalid` alone */
+    int64_t at_speed_clamp;  /* |v| component at MAX_SPEED = 50 (update.comp:5,199) */
+    double mass;             /* valid particles x particleMass (Fluid.cpp:210) */
+    double momentum[3];      /* m sum v */
+    double kinetic_energy;   /* m/2 sum |v|^2 */
+    double centre_of_mass[3];
+    double max_speed;
+    double density_min, density_max, density_mean;
+    double pressure_min, pressure_max, pressure_mean;
+    /* density / rest_density in bins of 1/WC_DIAG_HIST_PER_UNIT: [0,.25) [.25,.5) ... the
+     * last bin also takes everything above */
+    int64_t density_hist[WC_DIAG_HIST_BINS];
+    int64_t max_cell_count;  /* largest bin of the last sort, -1 if there is none */
+    int64_t nonempty_cells;  /* bins holding at least one particle, -1 likewise */
+} wc_diagnostics;
+int wc_diagnose(wc_handle* h, int32_t which, float rest_density, wc_diagnostics* out);
+
 /* Milliseconds per stage of the last wc_step (needs WC_FLAG_STAGE_TIMING; syncs). */
 int wc_stage_times(wc_handle* h, float ms[WC_NUM_STAGES]);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */

@@ -33,7 +33,7 @@ EXPORTS = (
     "wc_stage_times", "wc_launch_count", "wc_slab_get_view", "wc_slab_clear_recv",
     "wc_slab_sort_count", "wc_slab_sync_info", "wc_slab_reorder", "wc_slab_density",
     "wc_slab_update", "wc_advect_only", "wc_slab_ipc_export", "wc_slab_peer_open",
-    "wc_slab_peer_attach",
+    "wc_slab_peer_attach", "wc_diagnose",
 )
 
 
@@ -79,6 +79,21 @@ class SlabView(C.Structure):
         ("lc_recv", C.c_void_p * 2), ("pos_rho_sorted", C.c_void_p),
         ("vel_pres_sorted", C.c_void_p), ("mig_bytes", C.c_uint64), ("lc_bytes", C.c_uint64),
         ("owned_first", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+DIAG_HIST_BINS, DIAG_HIST_PER_UNIT = 32, 4
+
+
+class Diagnostics(C.Structure):
+    _fields_ = [
+        ("particles", C.c_int64), ("invalid", C.c_int64), ("out_of_box", C.c_int64),
+        ("at_speed_clamp", C.c_int64), ("mass", C.c_double), ("momentum", C.c_double * 3),
+        ("kinetic_energy", C.c_double), ("centre_of_mass", C.c_double * 3),
+        ("max_speed", C.c_double), ("density_min", C.c_double), ("density_max", C.c_double),
+        ("density_mean", C.c_double), ("pressure_min", C.c_double), ("pressure_max", C.c_double),
+        ("pressure_mean", C.c_double), ("density_hist", C.c_int64 * DIAG_HIST_BINS),
+        ("max_cell_count", C.c_int64), ("nonempty_cells", C.c_int64),
     ]
 
 
@@ -144,6 +159,7 @@ def lib():
             "wc_slab_ipc_export": [vp, C.POINTER(SlabIpc)],
             "wc_slab_peer_open": [vp, i32, C.POINTER(SlabIpc)],
             "wc_slab_peer_attach": [vp, i32, vp],
+            "wc_diagnose": [vp, i32, f32, C.POINTER(Diagnostics)],
         }
         for name, argtypes in sig.items():
             fn = getattr(L, name)
@@ -295,6 +311,17 @@ class Fluid:
 
     def sync(self):
         check(lib().wc_sync(self._h))
+
+    def diagnose(self, which=1) -> dict:
+        """wc_diagnose: on-device invalid counts, conserved quantities, density histogram."""
+        d = Diagnostics()
+        check(lib().wc_diagnose(self._h, int(which), float(self.step_params.rest_density),
+                                C.byref(d)))
+        out = {}
+        for name, ctype in Diagnostics._fields_:
+            v = getattr(d, name)
+            out[name] = np.array(v) if isinstance(v, C.Array) else v
+        return out
 
     # -- z-slab mode (see include/wc_sph.h, wc_slab_*)
     def slab_view(self) -> SlabView:

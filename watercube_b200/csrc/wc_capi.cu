@@ -6,6 +6,7 @@
 
 #include "../../include/wc_sph.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -13,6 +14,7 @@
 #include <new>
 
 #include "wc_common.cuh"
+#include "wc_diag.cuh"
 #include "wc_slab.cuh"
 #include "wc_sort.cuh"
 #include "wc_sph_tile.cuh"
@@ -115,6 +117,9 @@ struct wc_handle {
     uint32_t* counts = nullptr;
     unsigned long long* scan_status = nullptr;
     unsigned int* scan_counter = nullptr;
+
+    wc::DiagPartial* diag = nullptr;      // wc_diagnose scratch: [0] result, [1..] block partials
+    unsigned int* diag_cells = nullptr;   // [2]
 
     cudaEvent_t ev[WC_NUM_STAGES + 1] = {};
     bool have_times = false;
@@ -666,6 +671,8 @@ int wc_destroy(wc_handle* h) {
     cudaFree(h->nbr_mask);
     cudaFree(h->nbr_words);
     cudaFree(h->groups);
+    cudaFree(h->diag);
+    cudaFree(h->diag_cells);
     for (int k = 0; k < 2; k++) {
         cudaFree(h->mig_out[k]);
         cudaFree(h->mig_in[k]);
@@ -1145,6 +1152,69 @@ int wc_slab_peer_attach(wc_handle* h, int32_t direction, wc_handle* peer) {
     P.lc_recv = peer->lc_recv[1 - direction];
     P.sig = peer->sig;
     P.on = true;
+    return WC_OK;
+}
+
+int wc_diagnose(wc_handle* h, int32_t which, float rest_density, wc_diagnostics* out) {
+    if (!h || !out) return fail(WC_ERR_INVALID, "NULL argument");
+    if (which != 1 && which != 2) return fail(WC_ERR_INVALID, "which must be 1 or 2");
+    if (!(rest_density > 0.0f)) return fail(WC_ERR_INVALID, "rest_density must be positive");
+    WC_CUDA(cudaSetDevice(h->p.device));
+    if (!h->diag) {  // allocated on first use: most runs never ask
+        WC_CUDA(cudaMalloc(&h->diag, (size_t)(kDiagMaxBlocks + 1) * sizeof(DiagPartial)));
+        WC_CUDA(cudaMalloc(&h->diag_cells, 2 * sizeof(unsigned int)));
+    }
+    std::memset(out, 0, sizeof(*out));
+    out->particles = h->n;
+    out->max_cell_count = out->nonempty_cells = -1;
+    DiagPartial r;
+    std::memset(&r, 0, sizeof(r));
+    unsigned int cells[2] = {0u, 0u};
+    const bool have_cells = h->sorted_valid && !h->slab;
+    if (h->n > 0) {
+        const int first = which == 1 ? h->M : h->Cg;
+        // a fixed slice per block, so the fold order depends on n alone
+        const int blocks = (int)std::min<long long>(kDiagMaxBlocks, div_up(h->n, 4 * kDiagThreads));
+        const int per_block = div_up(h->n, blocks);
+        k_diag_particles<<<blocks, kDiagThreads, 0, h->stream>>>(
+            h->pos[which - 1] + first, h->vel[which - 1] + first, h->n, per_block, h->p.size,
+            1.0f / rest_density, h->diag + 1);
+        WC_CHECK_LAUNCH(h);
+        k_diag_fold<<<1, kDiagThreads, 0, h->stream>>>(h->diag + 1, blocks, h->diag);
+        WC_CHECK_LAUNCH(h);
+        WC_CUDA(cudaMemcpyAsync(&r, h->diag, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (have_cells) {
+        WC_CUDA(cudaMemsetAsync(h->diag_cells, 0, sizeof(cells), h->stream));
+        k_diag_cells<<<div_up(h->num_bins, 256), 256, 0, h->stream>>>(h->offsets, h->num_bins,
+                                                                     h->diag_cells);
+        WC_CHECK_LAUNCH(h);
+        WC_CUDA(cudaMemcpyAsync(cells, h->diag_cells, sizeof(cells), cudaMemcpyDeviceToHost,
+                                h->stream));
+    }
+    WC_CUDA(cudaStreamSynchronize(h->stream));
+    const double m = (double)h->d.particle_mass, nv = (double)r.valid;
+    out->invalid = (int64_t)r.invalid;
+    out->out_of_box = (int64_t)r.out_of_box;
+    out->at_speed_clamp = (int64_t)r.at_clamp;
+    out->mass = m * nv;
+    for (int a = 0; a < 3; a++) {
+        out->momentum[a] = m * r.mom[a];
+        out->centre_of_mass[a] = r.valid ? r.com[a] / nv : 0.0;
+    }
+    out->kinetic_energy = 0.5 * m * r.ke;
+    if (r.valid) {
+        out->max_speed = std::sqrt((double)r.vmax2);
+        out->density_min = r.rho_min, out->density_max = r.rho_max;
+        out->density_mean = r.rho_sum / nv;
+        out->pressure_min = r.pres_min, out->pressure_max = r.pres_max;
+        out->pressure_mean = r.pres_sum / nv;
+    }
+    for (int k = 0; k < WC_DIAG_HIST_BINS; k++) out->density_hist[k] = (int64_t)r.hist[k];
+    if (have_cells) {
+        out->max_cell_count = cells[0];
+        out->nonempty_cells = cells[1];
+    }
     return WC_OK;
 }
 

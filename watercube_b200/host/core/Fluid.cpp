@@ -50,6 +50,8 @@ Fluid::Fluid(const std::string& name)
       gravity_direction_(0.0f, -1.0f, 0.0f),  // :16
       has_mouse_ray_(false),
       user_particles_(false),
+      steps_(0),
+      time_(0.0),
       handle_(nullptr) {
     derived_ = wc_derived();
 }
@@ -135,8 +137,45 @@ FluidRef Fluid::setup() {
     sort_->attach(handle_);
     sort_->prepareBuffers();
     sort_->compileShaders();
+    steps_ = 0;
+    time_ = 0.0;
     util::log("fluid created\n");
     return shared_from_this();
+}
+
+void Fluid::saveCheckpoint(const std::string& path) {
+    if (!handle_) throw Error(WC_ERR_INVALID, "Fluid::saveCheckpoint before setup()");
+    util::CheckpointHeader h = util::CheckpointHeader();
+    h.grid_res = grid_res_;
+    h.size = size_;
+    h.particle_radius = particle_radius_;
+    h.time_scale = time_scale_;
+    h.steps = steps_;
+    h.time = time_;
+    util::saveCheckpoint(path, h, util::getParticles(particleBuffer1(), num_particles_));
+}
+
+FluidRef Fluid::restoreCheckpoint(const std::string& path) {
+    util::CheckpointHeader h;
+    std::vector<Particle> particles = util::loadCheckpoint(path, &h);
+    grid_res_ = h.grid_res;
+    size_ = h.size;
+    particle_radius_ = h.particle_radius;
+    time_scale_ = h.time_scale;
+    initial_particles_.swap(particles);
+    num_particles_ = (int)initial_particles_.size();
+    user_particles_ = true;
+    setup();
+    steps_ = h.steps;
+    time_ = h.time;
+    return shared_from_this();
+}
+
+wc_diagnostics Fluid::diagnostics(int which) {
+    if (!handle_) throw Error(WC_ERR_INVALID, "Fluid::diagnostics before setup()");
+    wc_diagnostics d;
+    util::check(wc_diagnose(handle_, which, rest_density_, &d));
+    return d;
 }
 
 void Fluid::reset() { setup(); }
@@ -184,6 +223,8 @@ void Fluid::update(double time) {
     if (!handle_) throw Error(WC_ERR_INVALID, "Fluid::update before setup()");
     const wc_step_params sp = stepParams();
     util::check(wc_step(handle_, (float)time, &sp));
+    steps_++;
+    time_ += time;
 }
 
 }  // namespace core

@@ -68,6 +68,16 @@ public:
     SortRef sort() const { return sort_; }
     wc_handle* nativeHandle() const { return handle_; }
 
+    // Checkpoint / resume: the state of buffer 1 with the setup-time parameters.
+    // restoreCheckpoint() configures the object from the file and calls setup(); the run then
+    // continues bit-identically to one that was never interrupted.
+    void saveCheckpoint(const std::string& path);
+    FluidRef restoreCheckpoint(const std::string& path);
+    uint64_t stepCount() const { return steps_; }
+    double simulatedTime() const { return time_; }
+    // On-device inspection of buffer 1 / 2 (what render modes 1-4 show).
+    wc_diagnostics diagnostics(int which = 1);
+
     // Derived constants of Fluid::setup (Fluid.cpp:206-216).
     float binSize() const { return derived_.bin_size; }
     float kernelRadius() const { return derived_.kernel_radius; }
@@ -92,6 +102,8 @@ protected:
     vec3 position_, camera_position_, light_position_, gravity_direction_;
     Ray mouse_ray_;
     bool has_mouse_ray_, user_particles_;
+    uint64_t steps_;
+    double time_;
     std::vector<Particle> initial_particles_;
     SortRef sort_;
     wc_handle* handle_;

@@ -3,6 +3,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 
 namespace core {
 namespace util {
@@ -78,6 +79,40 @@ void printParticles(Buffer particle_buffer, int n, float bin_size) {
             p.pressure, (int)(p.position.x / bin_size), (int)(p.position.y / bin_size),
             (int)(p.position.z / bin_size));
     }
+}
+
+static const char kMagic[8] = {'W', 'C', 'B', '2', '0', '0', 0, 0};
+
+void saveCheckpoint(const std::string& path, const CheckpointHeader& header,
+                    const std::vector<Particle>& particles) {
+    CheckpointHeader h = header;
+    std::memcpy(h.magic, kMagic, sizeof(kMagic));
+    h.version = 1;
+    h.num_particles = (int32_t)particles.size();
+    FILE* f = std::fopen(path.c_str(), "wb");
+    const bool ok = f && std::fwrite(&h, sizeof(h), 1, f) == 1 &&
+                    std::fwrite(particles.data(), sizeof(Particle), particles.size(), f) ==
+                        particles.size();
+    if (f && std::fclose(f) != 0) throw Error(WC_ERR_INVALID, "saveCheckpoint: cannot finish " + path);
+    if (!ok) throw Error(WC_ERR_INVALID, "saveCheckpoint: cannot write " + path);
+}
+
+std::vector<Particle> loadCheckpoint(const std::string& path, CheckpointHeader* header) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) throw Error(WC_ERR_INVALID, "loadCheckpoint: cannot open " + path);
+    CheckpointHeader h;
+    std::vector<Particle> particles;
+    bool ok = std::fread(&h, sizeof(h), 1, f) == 1 && std::memcmp(h.magic, kMagic, sizeof(kMagic)) == 0 &&
+              h.version == 1 && h.num_particles >= 0;
+    if (ok) {
+        particles.resize((size_t)h.num_particles);
+        ok = std::fread(particles.data(), sizeof(Particle), particles.size(), f) == particles.size() &&
+             std::fgetc(f) == EOF;  // a truncated or over-long file is not a checkpoint
+    }
+    std::fclose(f);
+    if (!ok) throw Error(WC_ERR_INVALID, "loadCheckpoint: " + path + " is not a version-1 checkpoint");
+    if (header) *header = h;
+    return particles;
 }
 
 }  // namespace util

@@ -87,5 +87,27 @@ std::vector<uint32_t> getUints(Buffer buffer, int num_items);             // uti
 // util.cpp:113-126: position, velocity, density, pressure, ivec3(position / binSize).
 void printParticles(Buffer particle_buffer, int n, float bin_size);
 
+// Checkpoint file: a 64-byte header followed by the 32-byte AoS records exactly as
+// getParticles returns them (util.cpp:42-63 layout), so `numpy.fromfile(f, float32,
+// offset=64).reshape(-1, 8)` reads it.  Buffer 1 keeps its order across save / restore, so a
+// restored run continues bit-identically (the stable sort only sees positions and order).
+struct CheckpointHeader {
+    char magic[8];          // "WCB200\0\0"
+    uint32_t version;       // 1
+    int32_t num_particles;
+    int32_t grid_res;
+    float size;
+    float particle_radius;
+    float time_scale;
+    uint64_t steps;         // Fluid::update calls that produced this state
+    double time;            // sum of the frame times passed to update()
+    uint8_t reserved[16];
+};
+static_assert(sizeof(CheckpointHeader) == 64, "checkpoint header is 64 bytes");
+
+void saveCheckpoint(const std::string& path, const CheckpointHeader& header,
+                    const std::vector<Particle>& particles);
+std::vector<Particle> loadCheckpoint(const std::string& path, CheckpointHeader* header);
+
 }  // namespace util
 }  // namespace core

@@ -4,6 +4,11 @@
 //
 //   wc_headless [--particles N] [--size S] [--grid G] [--steps K] [--device D] [--dump file]
 //               [--initial-only]   (write the initial lattice to --dump; no device needed)
+//               [--checkpoint file]  write a resumable checkpoint (header + AoS) after the run
+//               [--restore file]     start from a checkpoint instead of the initial lattice
+//
+// The statistics line is computed on the host from the downloaded buffer; its "device" object
+// is wc_diagnose's on-device reduction of the same buffer (they must agree).
 //
 // Exit code 0 on success, 2 when the native layer reports an error (e.g. no sm_100 device:
 // there is no CPU fallback).
@@ -14,6 +19,7 @@
 #include <cstring>
 
 #include "core/Fluid.h"
+#include "core/Scene.h"
 
 using namespace core;
 
@@ -21,6 +27,8 @@ int main(int argc, char** argv) {
     int n = 80000, grid = 21, steps = 100, device = 0;
     float size = 1.0f;
     const char* dump = nullptr;
+    const char* checkpoint = nullptr;
+    const char* restore = nullptr;
     bool initial_only = false;
     for (int i = 1; i < argc; i++) {
         auto next = [&](const char* flag) -> const char* {
@@ -34,6 +42,8 @@ int main(int argc, char** argv) {
         else if (const char* v = next("--steps")) steps = std::atoi(v);
         else if (const char* v = next("--device")) device = std::atoi(v);
         else if (const char* v = next("--dump")) dump = v;
+        else if (const char* v = next("--checkpoint")) checkpoint = v;
+        else if (const char* v = next("--restore")) restore = v;
         else if (std::strcmp(argv[i], "--initial-only") == 0) initial_only = true;
         else { std::fprintf(stderr, "unknown argument %s\n", argv[i]); return 1; }
     }
@@ -49,10 +59,17 @@ int main(int argc, char** argv) {
             std::fclose(f);
             return 0;
         }
-        fluid->setup();  // WaterCubeApp.cpp:59-62
+        if (restore) {
+            fluid->restoreCheckpoint(restore);  // configures from the file, then setup()
+            n = fluid->numParticles();
+        } else {
+            fluid->setup();  // WaterCubeApp.cpp:59-62
+        }
+        SceneRef scene = Scene::create();  // WaterCubeApp.cpp:64-66
+        scene->addObject(fluid);
         const double frame = 1.0 / 60.0;
         const auto t0 = std::chrono::steady_clock::now();
-        for (int s = 0; s < steps; s++) fluid->update(frame);  // Scene::update -> Fluid::update
+        for (int s = 0; s < steps; s++) scene->update(frame);  // Scene::update -> Fluid::update
         const std::vector<Particle> ps = util::getParticles(fluid->particleBuffer1(), n);  // syncs
         const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         double ke = 0, mom[3] = {0, 0, 0}, com[3] = {0, 0, 0}, vmax = 0;
@@ -70,11 +87,18 @@ int main(int argc, char** argv) {
                                p.position.y <= size && p.position.z >= 0 && p.position.z <= size);
             if (out || !std::isfinite(v2) || !(p.density > 0) || !std::isfinite(p.density)) bad++;
         }
-        std::printf("{\"particles\": %d, \"steps\": %d, \"seconds\": %.6f, \"updates_per_sec\": %.6g, "
+        const wc_diagnostics dg = fluid->diagnostics(1);
+        std::printf("{\"particles\": %d, \"steps\": %d, \"total_steps\": %llu, \"seconds\": %.6f, "
+                    "\"updates_per_sec\": %.6g, "
                     "\"kinetic_energy\": %.9g, \"momentum\": [%.9g, %.9g, %.9g], "
-                    "\"centre_of_mass\": [%.9g, %.9g, %.9g], \"max_speed\": %.9g, \"invalid\": %ld}\n",
-                    n, steps, secs, (double)n * steps / secs, ke, mom[0], mom[1], mom[2], com[0] / n,
-                    com[1] / n, com[2] / n, vmax, bad);
+                    "\"centre_of_mass\": [%.9g, %.9g, %.9g], \"max_speed\": %.9g, \"invalid\": %ld, "
+                    "\"device\": {\"kinetic_energy\": %.9g, \"invalid\": %lld, \"at_speed_clamp\": %lld, "
+                    "\"density_mean\": %.9g, \"max_cell_count\": %lld}}\n",
+                    n, steps, (unsigned long long)fluid->stepCount(), secs, (double)n * steps / secs, ke,
+                    mom[0], mom[1], mom[2], com[0] / n, com[1] / n, com[2] / n, vmax, bad,
+                    dg.kinetic_energy, (long long)dg.invalid, (long long)dg.at_speed_clamp,
+                    dg.density_mean, (long long)dg.max_cell_count);
+        if (checkpoint) fluid->saveCheckpoint(checkpoint);
         if (dump) {  // checkpoint: the 32-byte AoS array of util::getParticles (util.cpp:42-63)
             FILE* f = std::fopen(dump, "wb");
             if (!f || std::fwrite(ps.data(), sizeof(Particle), ps.size(), f) != ps.size()) {
