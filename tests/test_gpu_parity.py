@@ -361,6 +361,39 @@ def test_full_size_properties(capi, n):
         np.testing.assert_array_equal(fl.download(1), out1)
 
 
+@pytest.mark.parametrize("nb", [30, 50, 100, 200])
+def test_uniform_box_sweep_1m_subcase(capi, oracle, nb):
+    """BASELINE.json configs[4] (uniform random box, smoothing-length sweep) on its 1M sub-case
+    (SURVEY.md 8d): sort outputs and neighbour counts bit-exact against the oracle, density and
+    pressure within the fp32 tolerances, at ~30 / 50 / 100 / 200 neighbours per particle -- the
+    dense end overflows nothing: the list capacity follows the scene's number density."""
+    n = 1_000_000
+    h = scenes.smoothing_length_for_neighbours(float(nb))
+    size = float((n / (1.0 / 0.0175 ** 3)) ** (1.0 / 3.0))     # the lattice's number density
+    sc = scenes.uniform_box(n, size=size, h=h, seed=100 + nb)
+    p = oracle_params(oracle, sc)
+    d = oracle.derive(p)
+    s = oracle.sort(sc.particles, d.bin_size, p.grid_res)
+    P, nc = oracle.density(s["sorted"], s["counts"], s["offsets"], p, nthreads=oracle.max_threads())
+    P = oracle.as_f32(P)
+    assert 0.8 * nb < nc.mean() < 1.1 * nb                        # the sweep hits its target
+    with gpu_fluid(capi, sc, capi.FLAG_DEBUG_OUTPUTS) as fl:
+        fl.upload(sc.particles)
+        fl.sort_only()
+        fl.density_only()
+        got = fl.cells(neighbour_counts=True)
+        srt = fl.download(2)
+        fl.update_only(FRAME_DT)                                  # replays the list: must not fault
+        out = fl.download(1)
+    for key in ("cell_ids", "counts", "offsets", "perm"):
+        np.testing.assert_array_equal(got[key], s[key], err_msg=key)
+    np.testing.assert_array_equal(got["neighbour_counts"], nc)
+    wall = wall_term_magnitude(srt, sc.size, h)
+    assert np.all(np.abs(srt[:, 3] - P[:, 3]) <= RTOL_RHO * (np.abs(P[:, 3]) + wall))
+    assert np.all(np.abs(srt[:, 7] - P[:, 7]) <= RTOL_P * (np.abs(P[:, 7]) + 100.0))
+    assert np.isfinite(out).all()
+
+
 def test_neighbour_list_replay_equals_full_search(capi):
     """The update pass replays the density pass's neighbour list; with the list disabled,
     or too small (per-warp overflow -> that warp searches again), results are bit-identical."""
