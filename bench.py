@@ -229,9 +229,29 @@ def cpu_baseline(args, sc, budget_s=20.0):
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return {"value": sub.n * steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{steps} full steps of the {sub.n}-particle {args.workload} scene, "
-                      f"oracle/libwc_oracle.so, OpenMP {threads} threads, {dt:.1f} s"}
+    out = {"value": sub.n * steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
+           "sample": f"{steps} full steps of the {sub.n}-particle {args.workload} scene, "
+                     f"oracle/libwc_oracle.so, OpenMP {threads} threads, {dt:.1f} s"}
+    # per-stage split (all threads) and the single-threaded rate, one step each.
+    d = ob.derive(p)
+    frame_dt = np.float32(FRAME_DT) * np.float32(p.time_scale)
+
+    def staged(nthreads):
+        t = [time.perf_counter()]
+        srt = ob.sort(sub.particles, d.bin_size, p.grid_res)      # serial in the oracle
+        t.append(time.perf_counter())
+        P, _ = ob.density(srt["sorted"], srt["counts"], srt["offsets"], p, nthreads=nthreads)
+        t.append(time.perf_counter())
+        ob.update(P, srt["counts"], srt["offsets"], p, frame_dt, nthreads=nthreads)
+        t.append(time.perf_counter())
+        return [1e3 * (b - a) for a, b in zip(t[:-1], t[1:])]
+
+    ms = staged(threads)
+    out["stage_ms"] = {"bin_sort": ms[0], "density": ms[1], "update": ms[2]}
+    ms1 = staged(1)
+    out["single_thread"] = {"value": sub.n / (1e-3 * sum(ms1)), "unit": UNIT, "sample": "1 step",
+                            "stage_ms": {"bin_sort": ms1[0], "density": ms1[1], "update": ms1[2]}}
+    return out
 
 
 # ---------------------------------------------------------------------------- B200 arm
