@@ -225,28 +225,49 @@ int peer_signal(wc_handle* h, int d, int phase) {
     return WC_OK;
 }
 
-// First / last owned layer of buffer 2 -> the neighbours' ghost slots, then the signal.
-// The layer sent down becomes the lower neighbour's ghost-high slice (right after its owned
-// particles), the layer sent up the upper neighbour's ghost-low slice (right before them).
-int peer_push_halo(wc_handle* h, bool with_vel, int phase) {
-    if (!h->peer_mode()) return WC_OK;
-    int rc;
+// Where this rank's halo layers live in the attached neighbours (see PeerHalo).  The layer sent
+// down becomes the lower neighbour's ghost-high slice (right after its owned particles), the
+// layer sent up the upper neighbour's ghost-low slice (right before them).  Needs the counts
+// of wc_slab_sync_info.
+PeerHalo peer_halo(const wc_handle* h) {
+    PeerHalo ph = PeerHalo();
+    if (!h->peer_mode()) return ph;
+    ph.n_first = (uint32_t)h->n_first;
+    ph.hi_begin = (uint32_t)(h->n - h->n_last);
+    if (h->peer[0].on) {
+        ph.pos[0] = h->peer[0].pos1, ph.vel[0] = h->peer[0].vel1;
+        ph.dst[0] = (uint32_t)(h->Cg + h->peer[0].n_owned);
+    }
+    if (h->peer[1].on) {
+        ph.pos[1] = h->peer[1].pos1, ph.vel[1] = h->peer[1].vel1;
+        ph.dst[1] = (uint32_t)(h->Cg - h->n_last);
+    }
+    return ph;
+}
+
+// The same halo as explicit peer copies: only for the simple cross-check kernels
+// (WC_FLAG_SIMPLE_KERNELS), whose density pass has no remote stores.
+int peer_copy_halo(wc_handle* h) {
+    const PeerHalo ph = peer_halo(h);
     for (int d = 0; d < 2; d++) {
         if (!h->peer[d].on) continue;
         const size_t n_layer = (size_t)(d == 0 ? h->n_first : h->n_last);
-        const size_t src = (size_t)h->Cg + (d == 0 ? 0 : (size_t)(h->n - h->n_last));
-        const size_t dst = d == 0 ? (size_t)h->Cg + (size_t)h->peer[d].n_owned
-                                  : (size_t)h->Cg - n_layer;
-        if (n_layer > 0) {
-            WC_CUDA(cudaMemcpyAsync(h->peer[d].pos1 + dst, h->pos[1] + src, n_layer * sizeof(float4),
-                                    cudaMemcpyDeviceToDevice, h->stream));
-            if (with_vel)
-                WC_CUDA(cudaMemcpyAsync(h->peer[d].vel1 + dst, h->vel[1] + src,
-                                        n_layer * sizeof(float4), cudaMemcpyDeviceToDevice,
-                                        h->stream));
-        }
-        if ((rc = peer_signal(h, d, phase))) return rc;
+        const size_t src = (size_t)h->Cg + (d == 0 ? 0 : (size_t)ph.hi_begin);
+        if (n_layer == 0) continue;
+        WC_CUDA(cudaMemcpyAsync(ph.pos[d] + ph.dst[d], h->pos[1] + src, n_layer * sizeof(float4),
+                                cudaMemcpyDeviceToDevice, h->stream));
+        WC_CUDA(cudaMemcpyAsync(ph.vel[d] + ph.dst[d], h->vel[1] + src, n_layer * sizeof(float4),
+                                cudaMemcpyDeviceToDevice, h->stream));
     }
+    return WC_OK;
+}
+
+// Tells both attached neighbours that this step's `phase` data is in their buffers (the
+// producing kernel stored it there itself).
+int peer_signal_both(wc_handle* h, int phase) {
+    int rc;
+    for (int d = 0; d < 2; d++)
+        if (h->peer[d].on && (rc = peer_signal(h, d, phase))) return rc;
     return WC_OK;
 }
 
@@ -296,14 +317,11 @@ int sort_count_phase(wc_handle* h, bool timed) {
     WC_CHECK_LAUNCH(h);
     k_slab_info<<<div_up(G2, 256), 256, 0, h->stream>>>(h->counts, h->offsets, G2, h->Lz,
                                                        (uint32_t)h->Cg, h->info_dev,
-                                                       h->lc_send[0], h->lc_send[1]);
-    WC_CHECK_LAUNCH(h);
-    for (int d = 0; d < 2; d++) {  // peer mode: layer counts straight into the neighbours
-        if (!h->peer[d].on) continue;
-        WC_CUDA(cudaMemcpyAsync(h->peer[d].lc_recv, h->lc_send[d], h->lc_bytes,
-                                cudaMemcpyDeviceToDevice, h->stream));
-        if ((rc = peer_signal(h, d, kSigLc))) return rc;
-    }
+                                                       h->lc_send[0], h->lc_send[1],
+                                                       h->peer[0].on ? h->peer[0].lc_recv : nullptr,
+                                                       h->peer[1].on ? h->peer[1].lc_recv : nullptr);
+    WC_CHECK_LAUNCH(h);  // peer mode: the kernel stored the layer counts in the neighbours itself
+    if ((rc = peer_signal_both(h, kSigLc))) return rc;
     if (timed && (rc = record(h, 2))) return rc;
     h->info_valid = false;
     return WC_OK;
@@ -320,7 +338,8 @@ int sort_reorder_phase(wc_handle* h, bool timed, int n_in, int n_sorted) {
         WC_CHECK_LAUNCH(h);
         k_reorder<<<div_up(n_sorted, 256), 256, 0, h->stream>>>(
             h->ids, h->offsets, n_sorted, bin, G, h->pos[0], h->vel[0], h->pos[1] + h->Cg,
-            h->vel[1] + h->Cg, h->perm, h->zbase, (uint32_t)h->Cg);
+            h->vel[1] + h->Cg, h->perm, h->zbase, (uint32_t)h->Cg,
+            h->slab ? peer_halo(h) : PeerHalo());
         WC_CHECK_LAUNCH(h);
     }
     if (h->groups) {  // cut the owned rows into <= 32-particle groups for the gathers
@@ -354,7 +373,8 @@ int run_density(wc_handle* h, const wc_step_params& sp) {
     const bool simple = h->p.flags & WC_FLAG_SIMPLE_KERNELS;
     if (!simple)
         launch_density_tile(h->pos[1], h->vel[1], h->offsets, c, group_table(h),
-                            dbg ? h->neighbour_counts : nullptr, list, h->stream);
+                            dbg ? h->neighbour_counts : nullptr, list, h->stream,
+                            h->slab ? peer_halo(h) : PeerHalo());
     h->nbr_valid = !simple && h->nbr_idx != nullptr;
     if (simple) {
         if (dbg)
@@ -1015,7 +1035,7 @@ int wc_slab_reorder(wc_handle* h) {
     const int n_in = h->M + h->n_in_old + h->M;
     int rc = sort_reorder_phase(h, true, n_in, h->n);
     if (rc) return rc;
-    return peer_push_halo(h, false, kSigHaloPos);  // peer mode: halo positions
+    return peer_signal_both(h, kSigHaloPos);  // peer mode: k_reorder stored the halo remotely
 }
 
 int wc_slab_density(wc_handle* h, const wc_step_params* sp) {
@@ -1025,7 +1045,8 @@ int wc_slab_density(wc_handle* h, const wc_step_params* sp) {
     if (!h->sorted_valid) return fail(WC_ERR_INVALID, "wc_slab_density needs wc_slab_reorder");
     if ((rc = peer_wait(h, kSigHaloPos, h->step_no))) return rc;
     if ((rc = run_density(h, *sp))) return rc;
-    if ((rc = peer_push_halo(h, true, kSigHaloRho))) return rc;  // now carrying rho, P and v
+    if ((h->p.flags & WC_FLAG_SIMPLE_KERNELS) && h->peer_mode() && (rc = peer_copy_halo(h))) return rc;
+    if ((rc = peer_signal_both(h, kSigHaloRho))) return rc;  // rho, P stored remotely by the kernel
     return record(h, 4);
 }
 
@@ -1061,13 +1082,9 @@ int wc_slab_update(wc_handle* h, float frame_dt, const wc_step_params* sp) {
         WC_CHECK_LAUNCH(h);
         k_pack_migrants<<<div_up(n_layer > 0 ? n_layer : 1, 256), 256, 0, h->stream>>>(
             own_pos + start, own_vel + start, n_layer, flags, slots, h->M, h->mig_out[dir],
-            h->errors);
-        WC_CHECK_LAUNCH(h);
-        if (h->peer[dir].on) {  // peer mode: the message goes straight into the neighbour
-            WC_CUDA(cudaMemcpyAsync(h->peer[dir].mig_in, h->mig_out[dir], h->mig_bytes,
-                                    cudaMemcpyDeviceToDevice, h->stream));
-            if ((rc = peer_signal(h, dir, kSigMig))) return rc;
-        }
+            h->peer[dir].on ? h->peer[dir].mig_in : nullptr, h->errors);
+        WC_CHECK_LAUNCH(h);  // peer mode: the message went straight into the neighbour
+        if (h->peer[dir].on && (rc = peer_signal(h, dir, kSigMig))) return rc;
     }
     h->n_in_old = h->n;
     if ((rc = record(h, 5))) return rc;

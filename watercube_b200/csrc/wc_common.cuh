@@ -30,6 +30,19 @@ struct SphConsts {
     int mouse_hits;  // update.comp:118-121 evaluated on the host (all-uniform expression)
 };
 
+// Slab mode with attached neighbours (wc_slab_peer_*): where this rank's first / last owned
+// layer lives in the neighbours' buffer 2 (their ghost slots, mapped peer memory).  The kernels
+// that PRODUCE halo data store it there as they go -- the reorder writes positions and
+// velocities, the density pass adds density and pressure -- so the halo crosses NVLink under
+// the producing kernel and no copy sits between the phases.  All null / zero otherwise.
+struct PeerHalo {
+    float4* pos[2];     // [0] = the rank below, [1] = the rank above
+    float4* vel[2];
+    uint32_t dst[2];    // index of this rank's first halo particle in that neighbour's arrays
+    uint32_t n_first;   // owned sorted particles [0, n_first) are the lower halo
+    uint32_t hi_begin;  // owned sorted particles [hi_begin, n) are the upper halo
+};
+
 // count.comp:32, one component: clamp(int(p / binSize), 0, gridRes - 1) with an IEEE
 // fp32 divide and truncation toward zero.  Same float-side clamp as the oracle
 // (oracle/wc_oracle.cpp cell_coord) so NaN / huge inputs are defined identically.

@@ -76,19 +76,26 @@ k_hash_count_slab(const float4* __restrict__ pos, int total, int M, int n_old,
 __global__ void k_slab_info(const uint32_t* __restrict__ counts,
                             const uint32_t* __restrict__ offsets, int G2, int Lz, uint32_t Cg,
                             uint32_t* __restrict__ info, uint32_t* __restrict__ lc_down,
-                            uint32_t* __restrict__ lc_up) {
+                            uint32_t* __restrict__ lc_up, uint32_t* __restrict__ peer_down,
+                            uint32_t* __restrict__ peer_up) {
     const uint32_t n_own = offsets[(size_t)(Lz - 1) * G2] - Cg;
     const uint32_t n_first = offsets[(size_t)2 * G2] - Cg;
     const uint32_t n_last = n_own - (offsets[(size_t)(Lz - 2) * G2] - Cg);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // peer_down / peer_up: the neighbours' receive buffers (mapped peer memory) or null
     if (i == 0) {
         info[0] = n_own, info[1] = n_first, info[2] = n_last;
         lc_down[0] = n_first, lc_down[1] = n_own;
         lc_up[0] = n_last, lc_up[1] = n_own;
+        if (peer_down) peer_down[0] = n_first, peer_down[1] = n_own;
+        if (peer_up) peer_up[0] = n_last, peer_up[1] = n_own;
     }
     if (i < G2) {
-        lc_down[kLcHeader + i] = counts[(size_t)G2 + i];
-        lc_up[kLcHeader + i] = counts[(size_t)(Lz - 2) * G2 + i];
+        const uint32_t cd = counts[(size_t)G2 + i], cu = counts[(size_t)(Lz - 2) * G2 + i];
+        lc_down[kLcHeader + i] = cd;
+        lc_up[kLcHeader + i] = cu;
+        if (peer_down) peer_down[kLcHeader + i] = cd;
+        if (peer_up) peer_up[kLcHeader + i] = cu;
     }
 }
 
@@ -116,18 +123,26 @@ __global__ void k_flag_migrants(const float4* __restrict__ pos, int n, float bin
 __global__ void k_pack_migrants(const float4* __restrict__ pos, const float4* __restrict__ vel,
                                 int n, const uint32_t* __restrict__ flags,
                                 const uint32_t* __restrict__ slot, int cap,
-                                float4* __restrict__ msg, uint32_t* __restrict__ errors) {
+                                float4* __restrict__ msg, float4* __restrict__ peer_msg,
+                                uint32_t* __restrict__ errors) {
+    // peer_msg: the neighbour's mig_in (mapped peer memory) or null; gets the same message
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         const uint32_t total = slot[n];
         reinterpret_cast<uint32_t*>(msg)[0] = min(total, (uint32_t)cap);
+        if (peer_msg) reinterpret_cast<uint32_t*>(peer_msg)[0] = min(total, (uint32_t)cap);
         if (total > (uint32_t)cap) atomicAdd(errors, total - (uint32_t)cap);
     }
     if (i >= n || !flags[i]) return;
     const uint32_t s = slot[i];
     if (s >= (uint32_t)cap) return;
-    msg[kMigHeaderFloat4 + 2 * (size_t)s] = pos[i];
-    msg[kMigHeaderFloat4 + 2 * (size_t)s + 1] = vel[i];
+    const float4 p = pos[i], v = vel[i];
+    msg[kMigHeaderFloat4 + 2 * (size_t)s] = p;
+    msg[kMigHeaderFloat4 + 2 * (size_t)s + 1] = v;
+    if (peer_msg) {
+        peer_msg[kMigHeaderFloat4 + 2 * (size_t)s] = p;
+        peer_msg[kMigHeaderFloat4 + 2 * (size_t)s + 1] = v;
+    }
 }
 
 __global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256)
 k_reorder(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ offsets, int n, float bin,
           int G, const float4* __restrict__ pos_in, const float4* __restrict__ vel_in,
           float4* __restrict__ pos_out, float4* __restrict__ vel_out,
-          uint32_t* __restrict__ perm, int zbase, uint32_t base) {
+          uint32_t* __restrict__ perm, int zbase, uint32_t base, PeerHalo peer) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const uint32_t id = ids[j];
@@ -208,6 +208,16 @@ k_reorder(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ offsets
     pos_out[dst] = p;
     vel_out[dst] = v;
     perm[dst] = id;
+    // halo positions (+ velocities, which do not change before the update) straight into the
+    // neighbours' ghost slots
+    if (peer.pos[0] && dst < peer.n_first) {
+        peer.pos[0][peer.dst[0] + dst] = p;
+        peer.vel[0][peer.dst[0] + dst] = v;
+    }
+    if (peer.pos[1] && dst >= peer.hi_begin) {
+        peer.pos[1][peer.dst[1] + (dst - peer.hi_begin)] = p;
+        peer.vel[1][peer.dst[1] + (dst - peer.hi_begin)] = v;
+    }
 }
 
 }  // namespace wc

@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(kDensityWarps * 32, WC_DENSITY_MIN_BLOCKS)
 k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
                const uint32_t* __restrict__ offsets, SphConsts c,
                const uint4* __restrict__ groups, const uint32_t* __restrict__ num_groups,
-               uint32_t* __restrict__ neighbour_counts, NbrList list) {
+               uint32_t* __restrict__ neighbour_counts, NbrList list, PeerHalo peer) {
     __shared__ DensityStage s_stage[kDensityWarps];
     const int lane = threadIdx.x & 31;
     float4 p;
@@ -660,6 +660,17 @@ k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
     // In place like density.comp:135; the gather only reads x,y,z, which do not change.
     reinterpret_cast<float*>(pos_rho)[4 * (size_t)x.i + 3] = rho;
     reinterpret_cast<float*>(vel_pres)[4 * (size_t)x.i + 3] = pres;
+    // a halo particle: density and pressure also go into the neighbour's ghost copy (whose
+    // x,y,z and velocity the reorder already stored there)
+    const uint32_t t = (uint32_t)x.t;
+    if (peer.pos[0] && t < peer.n_first) {
+        reinterpret_cast<float*>(peer.pos[0])[4 * (size_t)(peer.dst[0] + t) + 3] = rho;
+        reinterpret_cast<float*>(peer.vel[0])[4 * (size_t)(peer.dst[0] + t) + 3] = pres;
+    }
+    if (peer.pos[1] && t >= peer.hi_begin) {
+        reinterpret_cast<float*>(peer.pos[1])[4 * (size_t)(peer.dst[1] + t - peer.hi_begin) + 3] = rho;
+        reinterpret_cast<float*>(peer.vel[1])[4 * (size_t)(peer.dst[1] + t - peer.hi_begin) + 3] = pres;
+    }
     if (kDebug) {  // the self pair was accepted iff the particle's own d2 is 0 (finite position)
         const bool self = dist2(p.x - p.x, p.y - p.y, p.z - p.z) < c.T;
         neighbour_counts[x.t] = acc.nn - (self ? 1u : 0u);
@@ -762,14 +773,15 @@ inline int blocks_for(int groups, int warps) { return (groups + warps - 1) / war
 
 inline void launch_density_tile(float4* pos_rho, float4* vel_pres, const uint32_t* offsets,
                                 const SphConsts& c, const GroupTable& gt,
-                                uint32_t* neighbour_counts, NbrList list, cudaStream_t stream) {
+                                uint32_t* neighbour_counts, NbrList list, cudaStream_t stream,
+                                const PeerHalo& peer = PeerHalo{}) {
     const int blocks = blocks_for(gt.max_groups, kDensityWarps);
     if (neighbour_counts)
         k_density_tile<true><<<blocks, kDensityWarps * 32, 0, stream>>>(
-            pos_rho, vel_pres, offsets, c, gt.groups, gt.count, neighbour_counts, list);
+            pos_rho, vel_pres, offsets, c, gt.groups, gt.count, neighbour_counts, list, peer);
     else
         k_density_tile<false><<<blocks, kDensityWarps * 32, 0, stream>>>(
-            pos_rho, vel_pres, offsets, c, gt.groups, gt.count, nullptr, list);
+            pos_rho, vel_pres, offsets, c, gt.groups, gt.count, nullptr, list, peer);
 }
 
 inline void launch_update_tile(const float4* pos_rho, const float4* vel_pres,
