@@ -251,6 +251,11 @@ typedef struct wc_slab_ipc {
     int32_t ghost_capacity;
 } wc_slab_ipc;
 int wc_slab_ipc_export(wc_handle* h, wc_slab_ipc* out);
+/* One whole step of a slab handle whose neighbours are all attached (or absent): the five
+ * phase calls above in one, so the host touches the step once; its only wait is the read of
+ * this step's particle counts (info as in wc_slab_sync_info, may be NULL).  A non-zero error
+ * count (capacity overflow, lost migrants) returns WC_ERR_CAPACITY. */
+int wc_slab_step_peer(wc_handle* h, float frame_dt, const wc_step_params* sp, int32_t info[8]);
 int wc_slab_peer_open(wc_handle* h, int32_t direction, const wc_slab_ipc* peer);
 int wc_slab_peer_attach(wc_handle* h, int32_t direction, wc_handle* peer);
 

@@ -33,7 +33,7 @@ EXPORTS = (
     "wc_stage_times", "wc_launch_count", "wc_slab_get_view", "wc_slab_clear_recv",
     "wc_slab_sort_count", "wc_slab_sync_info", "wc_slab_reorder", "wc_slab_density",
     "wc_slab_update", "wc_advect_only", "wc_slab_ipc_export", "wc_slab_peer_open",
-    "wc_slab_peer_attach", "wc_diagnose",
+    "wc_slab_peer_attach", "wc_diagnose", "wc_slab_step_peer",
 )
 
 
@@ -160,6 +160,7 @@ def lib():
             "wc_slab_peer_open": [vp, i32, C.POINTER(SlabIpc)],
             "wc_slab_peer_attach": [vp, i32, vp],
             "wc_diagnose": [vp, i32, f32, C.POINTER(Diagnostics)],
+            "wc_slab_step_peer": [vp, f32, C.POINTER(StepParams), C.POINTER(C.c_int32 * 8)],
         }
         for name, argtypes in sig.items():
             fn = getattr(L, name)
@@ -348,6 +349,13 @@ class Fluid:
 
     def slab_update(self, frame_dt=1.0 / 60.0):
         check(lib().wc_slab_update(self._h, float(frame_dt), C.byref(self.step_params)))
+
+    def slab_step_peer(self, frame_dt=1.0 / 60.0) -> dict:
+        """The five slab phases as one call (all neighbours attached); returns the step's info."""
+        info = (C.c_int32 * 8)()
+        check(lib().wc_slab_step_peer(self._h, float(frame_dt), C.byref(self.step_params),
+                                      C.byref(info)))
+        return dict(zip(SLAB_INFO, [int(x) for x in info]))
 
     # -- peer-memory exchange (include/wc_sph.h, wc_slab_peer_*)
     def slab_ipc_export(self) -> bytes:

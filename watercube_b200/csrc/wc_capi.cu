@@ -986,13 +986,9 @@ int wc_slab_sync_info(wc_handle* h, int32_t info[8]) {
     uint32_t* hi = h->info_host;
     int rcw = peer_wait(h, kSigLc, h->step_no);
     if (rcw) return rcw;
-    WC_CUDA(cudaMemcpyAsync(hi + 8, h->lc_recv[0] + 1, 4, cudaMemcpyDeviceToHost, h->stream));
-    WC_CUDA(cudaMemcpyAsync(hi + 9, h->lc_recv[1] + 1, 4, cudaMemcpyDeviceToHost, h->stream));
-    WC_CUDA(cudaMemcpyAsync(hi, h->info_dev, 12, cudaMemcpyDeviceToHost, h->stream));
-    WC_CUDA(cudaMemcpyAsync(hi + 3, h->lc_recv[0], 4, cudaMemcpyDeviceToHost, h->stream));
-    WC_CUDA(cudaMemcpyAsync(hi + 4, h->lc_recv[1], 4, cudaMemcpyDeviceToHost, h->stream));
-    WC_CUDA(cudaMemcpyAsync(hi + 5, h->errors, 4, cudaMemcpyDeviceToHost, h->stream));
-    WC_CUDA(cudaMemcpyAsync(hi + 6, h->m_in, 8, cudaMemcpyDeviceToHost, h->stream));
+    k_collect_info<<<1, 1, 0, h->stream>>>(h->info_dev, h->lc_recv[0], h->lc_recv[1], h->errors,
+                                           h->m_in, hi);  // hi is page-locked: a direct store
+    WC_CHECK_LAUNCH(h);
     WC_CUDA(cudaStreamSynchronize(h->stream));
     for (int k = 0; k < 8; k++) info[k] = (int32_t)hi[k];
     if ((int)hi[0] > h->cap)
@@ -1090,6 +1086,19 @@ int wc_slab_update(wc_handle* h, float frame_dt, const wc_step_params* sp) {
     if ((rc = record(h, 5))) return rc;
     h->have_times = (h->p.flags & WC_FLAG_STAGE_TIMING) != 0;
     return WC_OK;
+}
+
+int wc_slab_step_peer(wc_handle* h, float frame_dt, const wc_step_params* sp, int32_t info[8]) {
+    int32_t local[8];
+    int rc;
+    if ((rc = wc_slab_sort_count(h))) return rc;
+    if ((rc = wc_slab_sync_info(h, info ? info : local))) return rc;
+    if ((info ? info : local)[5] != 0)
+        return fail(WC_ERR_CAPACITY, "slab capacity overflow or lost migrants (%d)",
+                    (info ? info : local)[5]);
+    if ((rc = wc_slab_reorder(h))) return rc;
+    if ((rc = wc_slab_density(h, sp))) return rc;
+    return wc_slab_update(h, frame_dt, sp);
 }
 
 int wc_slab_ipc_export(wc_handle* h, wc_slab_ipc* out) {

@@ -99,6 +99,21 @@ __global__ void k_slab_info(const uint32_t* __restrict__ counts,
     }
 }
 
+// Everything wc_slab_sync_info hands to the host, gathered into one 10-word record that is
+// stored straight into page-locked host memory (one kernel instead of seven small copies in
+// the only host round trip of the step):
+// [n_own, n_first, n_last, ghost below, ghost above, errors, migrants in (2), neighbours' n_own (2)]
+__global__ void k_collect_info(const uint32_t* __restrict__ info, const uint32_t* __restrict__ lc_below,
+                               const uint32_t* __restrict__ lc_above,
+                               const uint32_t* __restrict__ errors,
+                               const uint32_t* __restrict__ m_in, uint32_t* __restrict__ host_out) {
+    host_out[0] = info[0], host_out[1] = info[1], host_out[2] = info[2];
+    host_out[3] = lc_below[0], host_out[4] = lc_above[0];
+    host_out[5] = *errors;
+    host_out[6] = m_in[0], host_out[7] = m_in[1];
+    host_out[8] = lc_below[1], host_out[9] = lc_above[1];
+}
+
 // Received layer counts -> the table's ghost layers.
 __global__ void k_install_ghost_counts(const uint32_t* __restrict__ lc_below,
                                        const uint32_t* __restrict__ lc_above, int G2, int Lz,

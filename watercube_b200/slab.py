@@ -157,7 +157,11 @@ def attach_peers_local(backends: Sequence["CudaSlabBackend"]):
 
 
 def run_step_peer(backend, frame_dt: float):
-    """One step of one rank in peer-memory mode (every rank runs this; no host exchange)."""
+    """One step of one rank in peer-memory mode (every rank runs this; no host exchange): the
+    five phases as ONE C-ABI call, wc_slab_step_peer."""
+    if hasattr(backend, "fluid"):
+        backend.info = backend.fluid.slab_step_peer(frame_dt)   # raises on capacity errors
+        return
     backend.sort_count()
     info = backend.sync_info()
     if info["errors"]:
