@@ -28,6 +28,9 @@ class OracleSlabBackend:
         self.info = None
 
     # -- data
+    def close(self):
+        pass
+
     def upload(self, particles):
         self.own = np.ascontiguousarray(particles, f32).reshape(-1, 8).copy()
 

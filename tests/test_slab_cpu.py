@@ -98,6 +98,34 @@ def test_virtual_ranks_equal_undecomposed_run(oracle, cuts):
         assert migrated > 0                                       # the test exercises migration
 
 
+def test_rebalance_virtual_ranks_continues_bit_identically(oracle):
+    """Re-cutting the slabs mid-run (cuts refreshed every k steps) changes nothing in
+    the results: 3 steps, re-cut, 3 more steps == 6 undecomposed steps, and the new cuts follow
+    the moved fluid."""
+    sc = make_scene()
+    p = oracle.default_params(num_particles=sc.n, size=sc.size, grid_res=sc.grid_res)
+    d = oracle.derive(p)
+    steps, world = 6, 3
+    ref = reference_run(oracle, sc, p, steps)
+    cuts = [0, 1, 2, 10]                                          # deliberately lopsided
+    parts = slab.decompose(sc.particles, cuts, d.bin_size, p.grid_res)
+    make = lambda z0, z1: OracleSlabBackend(oracle, p, z0, z1, migrant_capacity=2000)
+    backends = []
+    for r in range(world):
+        backends.append(make(cuts[r], cuts[r + 1]))
+        backends[-1].upload(parts[r])
+    for s in range(steps):
+        if s == 3:
+            before = [b.num_particles for b in backends]
+            cuts, backends = slab.rebalance_local(backends, make, d.bin_size, p.grid_res)
+            after = [b.num_particles for b in backends]
+            assert sum(after) == sc.n and max(after) - min(after) < max(before) - min(before)
+        drivers = [slab.SlabDriver(b, r, world) for r, b in enumerate(backends)]
+        slab.run_step_local(drivers, FRAME_DT)
+        buf1 = np.concatenate([b.download(1) for b in backends])
+        np.testing.assert_array_equal(buf1, ref[s][0], err_msg=f"state buffer, step {s}")
+
+
 # --------------------------------------------------------------------------- real gloo run
 def _free_port():
     with socket.socket() as s:
@@ -122,6 +150,11 @@ def _gloo_worker(rank, world, port, cuts, steps, out_dir):
         b.upload(parts[rank])
         drv = slab.SlabDriver(b, rank, world)
         for s in range(steps):
+            if s == 2:   # re-cut the slabs in the middle of the run (all-reduce + all-to-all)
+                make = lambda z0, z1: OracleSlabBackend(ob, p, z0, z1, migrant_capacity=2000)
+                new_cuts, b = slab.rebalance(b, rank, world, make, d.bin_size, p.grid_res)
+                assert new_cuts[0] == 0 and new_cuts[-1] == p.grid_res
+                drv = slab.SlabDriver(b, rank, world)
             slab.run_step(drv, FRAME_DT)
             np.save(os.path.join(out_dir, f"buf1_s{s}_r{rank}.npy"), b.download(1))
         dist.barrier()

@@ -114,6 +114,36 @@ def test_peer_memory_exchange_virtual_ranks_equal_whole_grid(capi, world):
         b.fluid.close()
 
 
+def test_rebalance_mid_run_equals_whole_grid(capi):
+    """Cuts refreshed in the middle of a run (slab.rebalance_local): fresh handles over the re-cut
+    state, peers re-attached; every step before and after still equals the whole-grid run."""
+    sc = make_scene(80000, seed=9)
+    steps, world = 8, 3
+    ref = whole_grid_run(capi, sc, steps)
+    d = capi.derive(capi.default_params(num_particles=sc.n, **scene_params(sc)))
+    cuts = [0, 3, 6, sc.grid_res]                                 # lopsided on purpose
+    parts = slab.decompose(sc.particles, cuts, d.bin_size, sc.grid_res)
+    make = lambda z0, z1: slab.CudaSlabBackend(scene_params(sc), z0, z1, capacity=sc.n,
+                                               ghost_capacity=sc.n, migrant_capacity=8192)
+    backends = []
+    for r in range(world):
+        backends.append(make(cuts[r], cuts[r + 1]))
+        backends[-1].upload(parts[r])
+    slab.attach_peers_local(backends)
+    for s in range(steps):
+        if s == 4:
+            before = [b.num_particles for b in backends]
+            cuts, backends = slab.rebalance_local(backends, make, d.bin_size, sc.grid_res)
+            slab.attach_peers_local(backends)
+            after = [b.num_particles for b in backends]
+            assert sum(after) == sc.n and max(after) - min(after) < max(before) - min(before)
+        slab.run_step_peer_local(backends, FRAME_DT)
+        buf1 = np.concatenate([b.download(1) for b in backends])
+        np.testing.assert_array_equal(buf1, ref[s][0], err_msg=f"state buffer, step {s}")
+    for b in backends:
+        b.close()
+
+
 def test_slab_capacity_overflow_is_reported(capi):
     sc = make_scene(20000)
     b = slab.CudaSlabBackend(scene_params(sc), 0, sc.grid_res, capacity=sc.n, ghost_capacity=16,

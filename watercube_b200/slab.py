@@ -64,6 +64,71 @@ def decompose(particles: np.ndarray, cuts: Sequence[int], bin_size: float, grid_
     return [np.ascontiguousarray(particles[rank_of == r]) for r in range(len(cuts) - 1)]
 
 
+# --------------------------------------------------------------------------- re-balancing
+# the cuts equalise particle counts from the per-layer histogram and are
+# refreshed every k steps, because the fluid moves along z.  Concatenating the ranks' buffer 1
+# (download(1)) in rank order IS the whole-grid state in the whole-grid order, and a cell
+# belongs to exactly one old rank, so re-cutting that concatenation and handing every new rank
+# its layers -- pieces taken in old-rank order -- continues the run bit-identically to one that
+# was never re-cut.  Pending migrant messages are duplicates of particles still present in the
+# senders' buffer 1; the fresh handles drop them.
+def recut_plan(particles: np.ndarray, layer_hist_global: np.ndarray, world: int, bin_size: float,
+               grid_res: int):
+    """-> (new cuts, destination rank of every particle of this piece)."""
+    cuts = slab_cuts(layer_hist_global, world)
+    lay = layer_of(particles[:, 2], bin_size, grid_res)
+    return cuts, np.searchsorted(np.asarray(cuts[1:-1]), lay, side="right")
+
+
+def rebalance_local(backends: Sequence, make_backend, bin_size: float, grid_res: int):
+    """Virtual ranks of one process: -> (new cuts, new backends).  make_backend(z0, z1) builds an
+    empty backend for the layers [z0, z1); the old ones are closed."""
+    world = len(backends)
+    state = np.concatenate([b.download(1) for b in backends])
+    hist = np.bincount(layer_of(state[:, 2], bin_size, grid_res), minlength=grid_res)
+    cuts = slab_cuts(hist, world)
+    parts = decompose(state, cuts, bin_size, grid_res)
+    for b in backends:
+        b.close()
+    fresh = []
+    for r in range(world):
+        nb = make_backend(cuts[r], cuts[r + 1])
+        nb.upload(parts[r])
+        fresh.append(nb)
+    return cuts, fresh
+
+
+def rebalance(backend, rank: int, world: int, make_backend, bin_size: float, grid_res: int,
+              device=None, group=None):
+    """One process per rank (torch.distributed): every rank calls this at the same step.
+    -> (new cuts, new backend).  The particles travel as one all-to-all of AoS records; the
+    histogram as one all-reduce.  Infrequent (every k >> 1 steps), so it goes through
+    download / upload rather than staying on the device."""
+    import torch
+    import torch.distributed as dist
+
+    mine = backend.download(1)
+    dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    hist = torch.from_numpy(np.bincount(layer_of(mine[:, 2], bin_size, grid_res),
+                                        minlength=grid_res).astype(np.int64)).to(dev)
+    dist.all_reduce(hist, group=group)
+    cuts, dest = recut_plan(mine, hist.cpu().numpy(), world, bin_size, grid_res)
+    order = np.argsort(dest, kind="stable")                  # by new owner, order kept inside
+    send_counts = np.bincount(dest, minlength=world).astype(np.int64)
+    sc = torch.from_numpy(send_counts).to(dev)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = rc.cpu().numpy()
+    send = torch.from_numpy(np.ascontiguousarray(mine[order])).to(dev).reshape(-1)
+    recv = torch.empty(int(recv_counts.sum()) * 8, dtype=torch.float32, device=dev)
+    dist.all_to_all_single(recv, send, [int(c) * 8 for c in recv_counts],
+                           [int(c) * 8 for c in send_counts], group=group)
+    backend.close()
+    nb = make_backend(cuts[rank], cuts[rank + 1])
+    nb.upload(recv.cpu().numpy().reshape(-1, 8))             # pieces arrive in old-rank order
+    return cuts, nb
+
+
 # --------------------------------------------------------------------------- driver
 @dataclass
 class Xfer:
@@ -291,6 +356,9 @@ class CudaSlabBackend:
             self.torch.cuda.synchronize(self.device)
         else:
             self.fluid.sync()
+
+    def close(self):
+        self.fluid.close()
 
     # -- exchange buffers
     def clear_recv(self, direction):
