@@ -290,8 +290,8 @@ def conserved(A, m):
 
 
 def test_default_scene_multi_step_statistics(capi, oracle):
-    """BASELINE config 1 (shortened to 40 steps for CI time; bench.py --config default runs
-    the 1000-step version): compare conserved / statistical quantities, not trajectories."""
+    """BASELINE config 1, first 40 steps with tight bounds (the full 1000 steps follow below):
+    compare conserved / statistical quantities, not trajectories."""
     sc = scenes.dam_break(80000, seed=0)
     steps = 40
     p = oracle_params(oracle, sc)
@@ -322,6 +322,48 @@ def test_default_scene_multi_step_statistics(capi, oracle):
     ks = np.max(np.abs(np.searchsorted(a, grid, side="right") / len(a)
                        - np.searchsorted(b, grid, side="right") / len(b)))
     assert ks < 0.02
+
+
+def test_default_scene_1000_steps_statistics(capi, oracle):
+    """BASELINE.json configs[0] in full: the WaterCube default scene (80 000 particles, unit
+    cube, G = 21), 1000 steps, checked against the CPU transcription on conserved and
+    statistical quantities at steps 100 / 500 / 1000 (trajectories are chaotic).  The bounds are
+    ~7x what two oracle runs differ by when one starts from positions moved by one ulp
+    (step 1000: kinetic energy 0.3 %, momentum 0.2 % of m sum|v|, centre of mass 1.2e-4, KS
+    distance of rho/rho0 0.004).  The GPU side of every scalar comes from wc_diagnose."""
+    sc = scenes.dam_break(80000, seed=0)
+    p = oracle_params(oracle, sc)
+    m = float(oracle.derive(p).particle_mass)
+    st = oracle.Stepper(sc.particles, p, nthreads=oracle.max_threads())
+    #            step: (kinetic, momentum / (m sum|v|), com, mean rho, KS)
+    bounds = {100: (1e-3, 1e-3, 1e-4, 1e-3, 0.01), 500: (1.5e-2, 1e-2, 1e-3, 5e-3, 0.03),
+              1000: (3e-2, 2e-2, 2e-3, 1e-2, 0.04)}
+    with gpu_fluid(capi, sc, 0) as fl:
+        fl.upload(sc.particles)
+        for s in range(1, 1001):
+            fl.step(FRAME_DT)
+            st.step(FRAME_DT)
+            if s not in bounds:
+                continue
+            tol_ke, tol_mom, tol_com, tol_rho, tol_ks = bounds[s]
+            dg = fl.diagnose(1)
+            G1 = fl.download(1)
+            co = conserved(oracle.as_f32(st.buf1), m)
+            assert dg["invalid"] == 0 and dg["out_of_box"] == 0, s       # particle.vert:36-46
+            assert dg["mass"] == pytest.approx(co["mass"], rel=1e-12)
+            assert abs(dg["kinetic_energy"] - co["kinetic"]) <= tol_ke * co["kinetic"], s
+            mom_scale = m * np.abs(oracle.as_f32(st.buf1)[:, 4:7]).sum()
+            assert np.all(np.abs(dg["momentum"] - co["momentum"]) <= tol_mom * mom_scale), s
+            assert np.all(np.abs(dg["centre_of_mass"] - co["com"]) <= tol_com), s
+            assert abs(dg["density_mean"] - co["rho"].mean()) <= tol_rho * co["rho"].mean(), s
+            assert abs(dg["at_speed_clamp"] / sc.n - (np.abs(oracle.as_f32(st.buf1)[:, 4:7]) >= 50.0)
+                       .any(1).mean()) <= 2e-3, s
+            assert dg["max_speed"] <= 50.0 * np.sqrt(3.0) + 1e-3           # update.comp:199
+            a, b = np.sort(G1[:, 3].astype(np.float64)), np.sort(co["rho"])
+            grid = np.concatenate([a, b])
+            ks = np.max(np.abs(np.searchsorted(a, grid, side="right") / len(a)
+                               - np.searchsorted(b, grid, side="right") / len(b)))
+            assert ks < tol_ks, (s, ks)
 
 
 # ------------------------------------------------------------------ BASELINE sizes: properties
