@@ -308,18 +308,20 @@ struct UpdateAcc {
     float Fpx = 0, Fpy = 0, Fpz = 0, Fvx = 0, Fvy = 0, Fvz = 0;
     uint32_t words_used = 0;  // words of the candidate sequence processed so far (no-list path)
 
-    // One accepted pair of update.comp:174-187; `on` = false turns the pair into a no-op
-    // (its operands are then stale registers).
+    // One accepted pair of update.comp:174-187.  A lane without a pick passes stale operands
+    // with 1/rho_j forced to zero, which makes the pair a no-op (`on` is informative only).
     __device__ __forceinline__ void pair(const SphConsts& c, float4 p, float4 v, float4 qa,
                                          float4 qb, bool on) {
         const float rx = p.x - qa.x, ry = p.y - qa.y, rz = p.z - qa.z;
         const float d2 = dist2(rx, ry, rz);
         const float inv_d = rsqrt_approx(fmaxf(d2, 1e-32f));  // Q7: dist == 0 -> r/d adds 0
         const float hd = c.h - d2 * inv_d;
+        // A lane without a pick has 1/rho_j = 0 (pick() zeroes it): S = 0 fails the test below
+        // and wv = 0, so the stale pair adds exactly zero without any select on `on`.
         const float S = (v.w + qb.w) * qa.w;                   // 2 * (Pi+Pj)/(2 rho_j)
-        const float w = (on && S > 0.0f) ? (S * (hd * hd)) * inv_d : 0.0f;  // Q9
+        const float w = (S > 0.0f) ? (S * (hd * hd)) * inv_d : 0.0f;  // Q9
         Fpx = fmaf(w, rx, Fpx), Fpy = fmaf(w, ry, Fpy), Fpz = fmaf(w, rz, Fpz);
-        const float wv = on ? hd * qa.w : 0.0f;                // update.comp:186-187
+        const float wv = hd * qa.w;                            // update.comp:186-187
         Fvx = fmaf(wv, qb.x - v.x, Fvx), Fvy = fmaf(wv, qb.y - v.y, Fvy),
         Fvz = fmaf(wv, qb.z - v.z, Fvz);
     }
@@ -353,6 +355,8 @@ struct UpdateAcc {
                 const float4* q = abase + (31 - lz);
                 qa = q[0];
                 qb = q[kReplaySlots];
+            } else {
+                qa.w = 0.0f;  // see pair()
             }
             m &= ~(0x80000000u >> (lz & 31));
             return on;
@@ -460,6 +464,8 @@ __device__ __forceinline__ void replay_ring(UpdateStage& st, UpdateAcc& acc,
             const float4* q = st.a + slot * 32 + (31 - lz);
             qa = q[0];
             qb = q[kReplaySlots];
+        } else {
+            qa.w = 0.0f;  // see UpdateAcc::pair()
         }
         m &= ~(0x80000000u >> (lz & 31));
         return on;
