@@ -312,7 +312,12 @@ struct UpdateAcc {
     // with 1/rho_j forced to zero, which makes the pair a no-op (`on` is informative only).
     __device__ __forceinline__ void pair(const SphConsts& c, float4 p, float4 v, float4 qa,
                                          float4 qb, bool on) {
-        const float rx = p.x - qa.x, ry = p.y - qa.y, rz = p.z - qa.z;
+        // x and y of the separation and of the velocity difference as packed pairs: the operands
+        // already sit in aligned register pairs (LDS.128 / LDG.128 results)
+        float rx, ry, dvx, dvy;
+        unpack2(sub2(pack2(p.x, p.y), pack2(qa.x, qa.y)), rx, ry);
+        unpack2(sub2(pack2(qb.x, qb.y), pack2(v.x, v.y)), dvx, dvy);
+        const float rz = p.z - qa.z;
         const float d2 = dist2(rx, ry, rz);
         const float inv_d = rsqrt_approx(fmaxf(d2, 1e-32f));  // Q7: dist == 0 -> r/d adds 0
         const float hd = c.h - d2 * inv_d;
@@ -322,8 +327,7 @@ struct UpdateAcc {
         const float w = (S > 0.0f) ? (S * (hd * hd)) * inv_d : 0.0f;  // Q9
         Fpx = fmaf(w, rx, Fpx), Fpy = fmaf(w, ry, Fpy), Fpz = fmaf(w, rz, Fpz);
         const float wv = hd * qa.w;                            // update.comp:186-187
-        Fvx = fmaf(wv, qb.x - v.x, Fvx), Fvy = fmaf(wv, qb.y - v.y, Fvy),
-        Fvz = fmaf(wv, qb.z - v.z, Fvz);
+        Fvx = fmaf(wv, dvx, Fvx), Fvy = fmaf(wv, dvy, Fvy), Fvz = fmaf(wv, qb.z - v.z, Fvz);
     }
 
     // Every lane walks its own accepted bits of the staged mask words [0, nwb) -- one flat
