@@ -172,6 +172,19 @@ __device__ __forceinline__ float warp_max_f(float v, bool use) {
     return ord2f(__reduce_max_sync(0xffffffffu, use ? f2ord(v) : 0u));
 }
 
+// Index of the most significant set bit (0xffffffff for 0), and the mask of the bits below an
+// index (all ones for an index >= 32): one instruction each (FLO, BMSK).
+__device__ __forceinline__ unsigned highest_bit(unsigned m) {
+    unsigned r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(m));
+    return r;
+}
+__device__ __forceinline__ unsigned bits_below(unsigned idx) {
+    unsigned r;
+    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(r) : "r"(0u), "r"(idx));
+    return r;
+}
+
 __device__ __forceinline__ float rsqrt_approx(float x) {
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -354,15 +367,15 @@ struct UpdateAcc {
                 mptr = (mptr == mend) ? mend : mptr + 32;
             }
             const bool on = m != 0u;
-            const int lz = __clz((int)m);  // 32 when no bit is left
+            const unsigned hb = highest_bit(m);  // 0xffffffff when no bit is left
             if (on) {
-                const float4* q = abase + (31 - lz);
+                const float4* q = abase + hb;
                 qa = q[0];
                 qb = q[kReplaySlots];
             } else {
                 qa.w = 0.0f;  // see pair()
             }
-            m &= ~(0x80000000u >> (lz & 31));
+            m &= bits_below(hb);  // drops bit hb (m stays 0 when it was 0)
             return on;
         };
         while (__any_sync(0xffffffffu, (m | mn) != 0u || mptr != mend)) {
@@ -463,15 +476,15 @@ __device__ __forceinline__ void replay_ring(UpdateStage& st, UpdateAcc& acc,
             m = st.mask[slot * 32 + lane];
         }
         const bool on = m != 0u;
-        const int lz = __clz((int)m);  // 32 when no bit is left
+        const unsigned hb = highest_bit(m);  // 0xffffffff when no bit is left
         if (on) {
-            const float4* q = st.a + slot * 32 + (31 - lz);
+            const float4* q = st.a + slot * 32 + hb;
             qa = q[0];
             qb = q[kReplaySlots];
         } else {
             qa.w = 0.0f;  // see UpdateAcc::pair()
         }
-        m &= ~(0x80000000u >> (lz & 31));
+        m &= bits_below(hb);
         return on;
     };
     for (;;) {
