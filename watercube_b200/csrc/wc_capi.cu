@@ -549,7 +549,8 @@ int wc_create(const wc_params* p, wc_handle** out) {
     const size_t nb = (size_t)h->num_bins;
     const size_t G2 = (size_t)p->grid_res * p->grid_res;
     const size_t in_slots = capz + 2 * (size_t)h->M;    // buffer 1: [M | owned | M]
-    const size_t sorted_slots = capz + 2 * (size_t)h->Cg;  // buffer 2: [Cg | owned | Cg]
+    // buffer 2: [Cg | owned | Cg] + the slack the cull's unconditional loads may read into
+    const size_t sorted_slots = capz + 2 * (size_t)h->Cg + (size_t)kCullOverread;
     auto scan_state_bytes = [](size_t elems) {
         const size_t tiles = (elems + kScanTile - 1) / kScanTile + 1;
         return (tiles * sizeof(unsigned long long) + 255) / 256 * 256 + 256;

@@ -60,6 +60,7 @@ constexpr int kUpdateWarps = WC_UPDATE_WARPS;  // warps per block, update pass (
 constexpr int kChunk = 128;                // staged candidates per density batch (4 words)
 constexpr int kCullDepth = 4;              // density pass: cull loads in flight per lane
 constexpr int kRing = 256;                 // density stage: ring of kChunk + 32 * kCullDepth slots
+constexpr int kCullOverread = 32 * kCullDepth;  // slack entries behind the sorted arrays (see gather_group)
 
 constexpr int kReplayWords = WC_REPLAY_WORDS;  // list words re-staged per update batch
 constexpr int kReplaySlots = kReplayWords * 32;
@@ -572,20 +573,20 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
         for (uint32_t j0 = __shfl_sync(full, sbeg, s); j0 < end; j0 += 32 * kDepth) {
             // kDepth x 32 candidates in flight, then culled against the targets' box grown
             // by h, 32 at a time, and ballot-compacted behind the pending ones
+            // The loads are unconditional (one base address, immediate offsets): a slice's last
+            // iteration reads up to kCullOverread - 1 entries past its end, which the buffers
+            // allow for; those lanes are dropped by the index test below.
             float4 q[kDepth];
+            const float4* src = pos_rho + j0 + lane;
 #pragma unroll
-            for (int k = 0; k < kDepth; k++) {
-                const uint32_t j = j0 + 32 * k + lane;
-                q[k] = make_float4(kFar, kFar, kFar, 0.0f);
-                if (j < end) q[k] = pos_rho[j];
-            }
+            for (int k = 0; k < kDepth; k++) q[k] = src[32 * k];
 #pragma unroll
             for (int k = 0; k < kDepth; k++) {
                 const uint32_t j = j0 + 32 * k + lane;
                 const float ex = fmaxf(fmaxf(bx0 - q[k].x, q[k].x - bx1), 0.0f);
                 const float ey = fmaxf(fmaxf(by0 - q[k].y, q[k].y - by1), 0.0f);
                 const float ez = fmaxf(fmaxf(bz0 - q[k].z, q[k].z - bz1), 0.0f);
-                const bool keep = ex * ex + ey * ey + ez * ez < Tcull;  // false for the filler
+                const bool keep = j < end && ex * ex + ey * ey + ez * ez < Tcull;
                 const unsigned km = __ballot_sync(full, keep);
                 if (keep) {
                     const int at = cnt + __popc(km & lt);
