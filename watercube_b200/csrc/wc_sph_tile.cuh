@@ -354,18 +354,25 @@ struct UpdateAcc {
     __device__ __forceinline__ void walk(const UpdateStage& st, int nwb, const SphConsts& c,
                                          float4 p, float4 v) {
         const int lane = threadIdx.x & 31;
-        const uint32_t* mptr = st.mask + lane;
-        const uint32_t* const mend = mptr + 32 * nwb;  // a zero row
-        unsigned m = mptr[0], mn = (nwb > 1) ? mptr[32] : 0u;
-        mptr = (nwb > 2) ? mptr + 64 : mend;
+        // the mask words are addressed through ONE 32-bit shared-memory address (a generic pointer
+        // costs a second induction variable for the end test)
+        uint32_t mptr = (uint32_t)__cvta_generic_to_shared(st.mask + lane);
+        const uint32_t mend = mptr + 128u * (uint32_t)nwb;  // a zero row
+        auto lds_u32 = [](uint32_t a) -> unsigned {
+            unsigned r;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+            return r;
+        };
+        unsigned m = lds_u32(mptr), mn = (nwb > 1) ? lds_u32(mptr + 128u) : 0u;
+        mptr = (nwb > 2) ? mptr + 256u : mend;
         const float4* abase = st.a;  // slot 0 of the word being drained
         float4 qa0 = make_float4(0, 0, 0, 0), qb0 = qa0, qa1 = qa0, qb1 = qa0;
         auto pick = [&](float4& qa, float4& qb) -> bool {
             if (m == 0u) {
                 m = mn;
                 abase += 32;
-                mn = *mptr;
-                mptr = (mptr == mend) ? mend : mptr + 32;
+                mn = lds_u32(mptr);
+                mptr = (mptr == mend) ? mend : mptr + 128u;
             }
             const bool on = m != 0u;
             const unsigned hb = highest_bit(m);  // 0xffffffff when no bit is left
