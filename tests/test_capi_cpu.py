@@ -36,6 +36,29 @@ def test_library_exports_every_declared_symbol(capi):
     assert L.wc_abi_version() == 1
 
 
+def test_header_is_plain_c_and_sizes_agree(capi, tmp_path):
+    """The drop-in boundary is a C ABI: include/wc_sph.h compiles as strict C99, and the struct
+    sizes the C compiler sees are the ones the ctypes mirror uses."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "wc_sph.h"\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(wc_params), '
+        'sizeof(wc_step_params), sizeof(wc_derived), sizeof(wc_particle), sizeof(wc_device_view), '
+        'sizeof(wc_slab_view), sizeof(wc_slab_ipc), sizeof(wc_diagnostics)); return 0; }\n')
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror",
+                    "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True,
+                                          check=True).stdout.split()]
+    want = [C.sizeof(t) for t in (capi.Params, capi.StepParams, capi.Derived)] + \
+           [capi.PARTICLE_DTYPE.itemsize] + \
+           [C.sizeof(t) for t in (capi.DeviceView, capi.SlabView, capi.SlabIpc, capi.Diagnostics)]
+    assert got == want
+
+
 def test_struct_layouts_match_header(capi):
     assert C.sizeof(capi.Params) == 64          # 13 x 4 bytes, padding, pointer
     assert C.sizeof(capi.StepParams) == 52
