@@ -56,6 +56,14 @@ constexpr int kDensityWarps = WC_DENSITY_WARPS;  // warps (= groups) per block, 
 #ifndef WC_WALK_RING
 #define WC_WALK_RING 0
 #endif
+// Pair-loop iterations (two pairs each) per all-lanes-done test of the walk.
+#ifndef WC_WALK_UNROLL
+#define WC_WALK_UNROLL 1
+#endif
+// 1: drop every target's own pair from the replayed masks (it adds exactly zero force).
+#ifndef WC_DROP_SELF
+#define WC_DROP_SELF 1
+#endif
 constexpr int kUpdateWarps = WC_UPDATE_WARPS;  // warps per block, update pass (6 KB stage each)
 constexpr int kChunk = 128;                // staged candidates per density batch (4 words)
 constexpr int kCullDepth = 4;              // density pass: cull loads in flight per lane
@@ -387,10 +395,13 @@ struct UpdateAcc {
             return on;
         };
         while (__any_sync(0xffffffffu, (m | mn) != 0u || mptr != mend)) {
-            const bool on0 = pick(qa0, qb0);
-            const bool on1 = pick(qa1, qb1);
-            pair(c, p, v, qa0, qb0, on0);
-            pair(c, p, v, qa1, qb1, on1);
+#pragma unroll
+            for (int rep = 0; rep < WC_WALK_UNROLL; rep++) {
+                const bool on0 = pick(qa0, qb0);
+                const bool on1 = pick(qa1, qb1);
+                pair(c, p, v, qa0, qb0, on0);
+                pair(c, p, v, qa1, qb1, on1);
+            }
         }
     }
 
@@ -763,6 +774,7 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
                 }
             }
             __syncwarp();
+#if WC_DROP_SELF
             // a listed candidate that is one of this group's own targets: drop that target's
             // self pair (it would add exactly zero; this only saves the evaluation)
 #pragma unroll
@@ -771,6 +783,7 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
                 if (t < 32u) atomicAnd(&st.mask[u * 32 + t], ~(1u << lane));
             }
             __syncwarp();
+#endif
             acc.walk(st, (int)min((uint32_t)kReplayWords, nw - w0), c, p, v);
             __syncwarp();
         }
