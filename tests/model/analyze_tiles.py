@@ -3,7 +3,7 @@ per 32-target warp, for a cell-sorted scene.  Used to choose grouping and cull s
 without spending GPU time."""
 import sys, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import binding as ob
 from watercube_b200 import scenes
 

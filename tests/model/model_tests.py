@@ -4,14 +4,14 @@ designs that would test fewer -- per-lane cell-column windows inside the same gr
 row-aligned 16-target groups -- and against the true neighbour count.  DESIGN.md "where the next
 factor would come from" quotes these numbers.
 
-    python tools/model_tests.py [particles] [steps before measuring]
+    python tests/model/model_tests.py [particles] [steps before measuring]
 """
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import binding as ob            # noqa: E402  (tools may use the checker)
 from watercube_b200 import scenes           # noqa: E402
 

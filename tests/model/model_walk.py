@@ -3,14 +3,14 @@ iterations per 32-target group for different ways of batching the neighbour-list
 Every lane drains its own accepted bits two per iteration and lanes only wait for each other
 at a batch's end, so iterations/batch = max over lanes of ceil(bits / 2).
 
-    python tools/model_walk.py [n] [steps]
+    python tests/model/model_walk.py [n] [steps]
 """
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import binding as ob  # noqa: E402
 from watercube_b200 import scenes  # noqa: E402
 

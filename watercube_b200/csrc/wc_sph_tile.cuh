@@ -429,7 +429,7 @@ struct UpdateAcc {
 
 // ---------------------------------------------------------------------------------------
 // Ring replay of a group's neighbour list (update pass).  With hard batches every lane waits at
-// each batch's end for the lane with the most accepted bits in that batch (tools/model_walk.py:
+// each batch's end for the lane with the most accepted bits in that batch (tests/model/model_walk.py:
 // 41 pair-loop iterations per group at 5 words against 25 for the whole list at once).  Here
 // the stage holds the R = kReplayWords most recent list words as a ring: a lane drains its own
 // bits word after word and may run ahead of the slowest lane by the resident window; once every
