@@ -83,6 +83,9 @@ def lib():
         L.wco_density_f64.argtypes = [vp, i32, vp, vp, C.POINTER(Params), vp, vp, i32]
         L.wco_update_f64.argtypes = [vp, vp, vp, i32, vp, vp, C.POINTER(Params), f32, vp, vp, vp,
                                      i32]
+        L.wco_update_f64_scaled.argtypes = [vp, vp, vp, i32, vp, vp, C.POINTER(Params), f32, vp, vp,
+                                            vp, vp, i32]
+        L.wco_update_f64_scaled.restype = None
         L.wco_max_threads.restype = i32
         for f in ("wco_default_params", "wco_derive", "wco_cell_ids", "wco_sort", "wco_density",
                   "wco_update", "wco_step", "wco_advect", "wco_density_f64", "wco_update_f64"):
@@ -211,6 +214,31 @@ def update_f64(in_particles, rho, pres, counts, offsets, params: Params, dt, nth
     lib().wco_update_f64(_ptr(P), _ptr(rho), _ptr(pres), n, _ptr(counts), _ptr(offsets),
                          C.byref(params), float(dt), _ptr(F), _ptr(v), _ptr(x), int(nthreads))
     return F, v, x
+
+
+def update_f64_scaled(in_particles, rho, pres, counts, offsets, params: Params, dt, nthreads=1):
+    """update_f64 plus, per particle and component, the sum of the magnitudes of all terms
+    added into F (the scale rounding errors are proportional to).  -> (F, v, x, scale)"""
+    P = as_particles(in_particles)
+    n = P.shape[0]
+    F = np.empty((n, 3), np.float64)
+    v = np.empty((n, 3), np.float64)
+    x = np.empty((n, 3), np.float64)
+    S = np.empty((n, 3), np.float64)
+    lib().wco_update_f64_scaled(_ptr(P), _ptr(rho), _ptr(pres), n, _ptr(counts), _ptr(offsets),
+                                C.byref(params), float(dt), _ptr(F), _ptr(v), _ptr(x), _ptr(S),
+                                int(nthreads))
+    return F, v, x, S
+
+
+def host_threads() -> int:
+    """Processors this process may run on (not OMP_NUM_THREADS, which torchrun sets to 1)."""
+    import os
+
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def advect(particles, size, dt):

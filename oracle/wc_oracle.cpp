@@ -263,12 +263,15 @@ template <typename T, typename RhoAt, typename PresAt>
 inline void update_one(const wco_particle* P, int i, const uint32_t* counts,
                        const uint32_t* offsets, const Consts<T>& c, float bin_f, float h_f,
                        bool mouse_hits, T dt, RhoAt rho_at, PresAt pres_at, T* force_out,
-                       T* vel_out, T* pos_out) {
+                       T* vel_out, T* pos_out, T* term_scale_out = nullptr) {
     const T rho_i = rho_at(i), pres_i = pres_at(i);
     T pos[3] = {(T)P[i].position[0], (T)P[i].position[1], (T)P[i].position[2]};
     T vel_i[3] = {(T)P[i].velocity[0], (T)P[i].velocity[1], (T)P[i].velocity[2]};
     T Fp[3] = {0, 0, 0}, Fv[3] = {0, 0, 0};
     T ext[3] = {c.g[0] * rho_i, c.g[1] * rho_i, c.g[2] * rho_i};  // update.comp:145 (Q8)
+    // test aid, not reference math: per component, the sum of the MAGNITUDES of everything
+    // that is added into F -- the scale rounding errors of the sum are proportional to
+    T S[3] = {std::abs(ext[0]), std::abs(ext[1]), std::abs(ext[2])};
 
     for_each_neighbour(
         P, i, counts, offsets, bin_f, h_f, c.G,
@@ -288,6 +291,8 @@ inline void update_one(const wco_particle* P, int i, const uint32_t* counts,
                 T w[3];
                 spiky(c, r, d + c.eps, w);  // update.comp:181 (Q7)
                 for (int a = 0; a < 3; a++) Fp[a] -= (c.m * pr) * w[a];
+                if (term_scale_out)
+                    for (int a = 0; a < 3; a++) S[a] += std::abs((c.m * pr) * w[a]);
             }
             // update.comp:186-187
             const T wv = wvis(c, d);
@@ -295,13 +300,21 @@ inline void update_one(const wco_particle* P, int i, const uint32_t* counts,
                 const T vd = (T)P[j].velocity[a] - vel_i[a];
                 Fv[a] += (c.m * (vd / rho_j)) * wv;
             }
+            if (term_scale_out)  // both velocities enter the difference with their own rounding
+                for (int a = 0; a < 3; a++)
+                    S[a] += c.mu * std::abs((c.m * ((std::abs((T)P[j].velocity[a]) +
+                                                     std::abs(vel_i[a])) / rho_j)) * wv);
         });
 
     // update.comp:191
     T mf[3] = {0, 0, 0}, wf[3];
     if (mouse_hits) mouse_force(c, pos, pres_i, mf);
     wall_forces(c, pos, wf);
-    for (int a = 0; a < 3; a++) ext[a] += mf[a] + wf[a];
+    for (int a = 0; a < 3; a++) {
+        ext[a] += mf[a] + wf[a];
+        S[a] += std::abs(mf[a]) + std::abs(wf[a]);
+        if (term_scale_out) term_scale_out[a] = S[a];
+    }
 
     T F[3], v[3], x[3];
     for (int a = 0; a < 3; a++) {
@@ -333,8 +346,10 @@ inline void update_one(const wco_particle* P, int i, const uint32_t* counts,
 
 inline int clamp_threads(int nthreads) {
 #ifdef _OPENMP
+    // The caller's explicit count wins over OMP_NUM_THREADS (torchrun exports 1 to its
+    // workers); it is only capped by the processors this process may run on.
     if (nthreads < 1) nthreads = 1;
-    const int mx = omp_get_max_threads();
+    const int mx = omp_get_num_procs();
     return nthreads > mx ? mx : nthreads;
 #else
     (void)nthreads;
@@ -526,6 +541,14 @@ void wco_update_f64(const wco_particle* in, const double* density, const double*
                     int32_t n, const uint32_t* counts, const uint32_t* offsets,
                     const wco_params* p, float dt, double* forces, double* vel, double* pos,
                     int32_t nthreads) {
+    wco_update_f64_scaled(in, density, pressure, n, counts, offsets, p, dt, forces, vel, pos,
+                          nullptr, nthreads);
+}
+
+void wco_update_f64_scaled(const wco_particle* in, const double* density, const double* pressure,
+                           int32_t n, const uint32_t* counts, const uint32_t* offsets,
+                           const wco_params* p, float dt, double* forces, double* vel, double* pos,
+                           double* term_scale, int32_t nthreads) {
     const Consts<double> c = make_consts<double>(p);
     const Consts<float> cf = make_consts<float>(p);
     const bool hits = mouse_ray_hits_box(p);
@@ -536,7 +559,8 @@ void wco_update_f64(const wco_particle* in, const double* density, const double*
         update_one<double>(
             in, i, counts, offsets, c, cf.bin, cf.h, hits, (double)dt,
             [&](uint32_t j) { return density[j]; }, [&](uint32_t j) { return pressure[j]; },
-            forces ? &forces[3 * (size_t)i] : nullptr, &vel[3 * (size_t)i], &pos[3 * (size_t)i]);
+            forces ? &forces[3 * (size_t)i] : nullptr, &vel[3 * (size_t)i], &pos[3 * (size_t)i],
+            term_scale ? &term_scale[3 * (size_t)i] : nullptr);
     }
 }
 

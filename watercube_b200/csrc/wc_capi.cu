@@ -97,6 +97,9 @@ struct wc_handle {
     uint32_t* ranks = nullptr;
     uint32_t* ids = nullptr;              // arrival-ordered IDs (sort.comp's raw output)
     uint32_t* perm = nullptr;             // stable permutation: perm[dst] = src
+    uint32_t* big_cells = nullptr;        // cells above kBigCell particles (k_reorder_big)
+    uint32_t* big_count = nullptr;        // (in the arena: zero at the start of every sort)
+    int big_cap = 0;
     uint32_t* offsets = nullptr;          // num_bins + 1
     uint32_t* neighbour_counts = nullptr;
     float4* forces = nullptr;
@@ -336,10 +339,19 @@ int sort_reorder_phase(wc_handle* h, bool timed, int n_in, int n_sorted) {
         k_scatter_ids<<<div_up(n_in, 256), 256, 0, h->stream>>>(h->cell_ids, h->ranks, h->offsets,
                                                                  n_in, h->ids, (uint32_t)h->Cg);
         WC_CHECK_LAUNCH(h);
+        const ReorderIO io{h->pos[0], h->vel[0], h->pos[1] + h->Cg, h->vel[1] + h->Cg, h->perm,
+                           h->slab ? peer_halo(h) : PeerHalo()};
         k_reorder<<<div_up(n_sorted, 256), 256, 0, h->stream>>>(
-            h->ids, h->offsets, n_sorted, bin, G, h->pos[0], h->vel[0], h->pos[1] + h->Cg,
-            h->vel[1] + h->Cg, h->perm, h->zbase, (uint32_t)h->Cg,
-            h->slab ? peer_halo(h) : PeerHalo());
+            h->ids, h->offsets, n_sorted, bin, G, h->zbase, (uint32_t)h->Cg, io, h->big_cells,
+            h->big_count, (uint32_t)h->big_cap);
+        WC_CHECK_LAUNCH(h);
+        // cells above kBigCell particles (none in a physical scene: the kernel then exits at
+        // once): radix-sorted per cell; IDs index the (virtual) input, hence the pass count
+        int bits = 1;
+        while (bits < 32 && (1ll << bits) < (long long)n_in) bits++;
+        k_reorder_big<<<kBigBlocks, kBigThreads, 0, h->stream>>>(
+            h->ids, h->ranks, h->offsets, (uint32_t)h->Cg, io, h->big_cells, h->big_count,
+            (uint32_t)h->big_cap, (bits + 7) / 8);
         WC_CHECK_LAUNCH(h);
     }
     if (h->groups) {  // cut the owned rows into <= 32-particle groups for the gathers
@@ -583,6 +595,8 @@ int wc_create(const wc_params* p, wc_handle** out) {
     WC_ALLOC(h->ranks, in_slots * sizeof(uint32_t));
     WC_ALLOC(h->ids, capz * sizeof(uint32_t));
     WC_ALLOC(h->perm, capz * sizeof(uint32_t));
+    h->big_cap = cap / kBigCell + 1;      // more cells than this cannot exceed kBigCell each
+    WC_ALLOC(h->big_cells, (size_t)h->big_cap * sizeof(uint32_t));
     WC_ALLOC(h->offsets, (nb + 1) * sizeof(uint32_t));
     WC_ALLOC(h->arena, h->arena_bytes);
     if (!(p->flags & WC_FLAG_SIMPLE_KERNELS)) {
@@ -612,6 +626,7 @@ int wc_create(const wc_params* p, wc_handle** out) {
     h->scan_status = (unsigned long long*)((char*)h->arena + counts_bytes);
     h->scan_counter = (unsigned int*)((char*)h->arena + counts_bytes + status_bytes);
     h->num_groups = (uint32_t*)((char*)h->arena + counts_bytes + status_bytes + 128);
+    h->big_count = (uint32_t*)((char*)h->arena + counts_bytes + status_bytes + 192);
     if (slab) {
         size_t off = x_off0;
         for (int k = 0; k < 4; k++) {
@@ -684,6 +699,7 @@ int wc_destroy(wc_handle* h) {
     cudaFree(h->ranks);
     cudaFree(h->ids);
     cudaFree(h->perm);
+    cudaFree(h->big_cells);
     cudaFree(h->offsets);
     cudaFree(h->arena);
     cudaFree(h->neighbour_counts);

@@ -190,33 +190,139 @@ k_scatter_ids(const uint32_t* __restrict__ cell_ids, const uint32_t* __restrict_
 // slice that are smaller: that is the stable rank (what the serial oracle loop produces).
 // Threads of one cell walk the same slice in lockstep, so the loads are warp broadcasts.
 // The payload moves as two float4 (SoA), and the permutation is kept (sort.comp's output).
+// The in-cell count is quadratic in the cell's occupancy, which is fine at the reference's
+// ~20 particles per cell; a cell holding more than kBigCell particles (all particles piled
+// into a few cells, NaN positions collapsing into cell 0, gridRes of 1..few) is only
+// registered here and handled by k_reorder_big.
+constexpr int kBigCell = 256;
+constexpr int kBigThreads = 1024;
+constexpr int kBigBlocks = 296;  // 2 x 148 SMs; blocks stride over the registered cells
+
+struct ReorderIO {
+    const float4* pos_in;
+    const float4* vel_in;
+    float4* pos_out;
+    float4* vel_out;
+    uint32_t* perm;
+    PeerHalo peer;
+};
+
+__device__ __forceinline__ void reorder_store(const ReorderIO& io, uint32_t dst, uint32_t id) {
+    const float4 p = io.pos_in[id];
+    const float4 v = io.vel_in[id];
+    io.pos_out[dst] = p;
+    io.vel_out[dst] = v;
+    io.perm[dst] = id;
+    // halo positions (+ velocities, which do not change before the update) straight into the
+    // neighbours' ghost slots
+    if (io.peer.pos[0] && dst < io.peer.n_first) {
+        io.peer.pos[0][io.peer.dst[0] + dst] = p;
+        io.peer.vel[0][io.peer.dst[0] + dst] = v;
+    }
+    if (io.peer.pos[1] && dst >= io.peer.hi_begin) {
+        io.peer.pos[1][io.peer.dst[1] + (dst - io.peer.hi_begin)] = p;
+        io.peer.vel[1][io.peer.dst[1] + (dst - io.peer.hi_begin)] = v;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_reorder(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ offsets, int n, float bin,
-          int G, const float4* __restrict__ pos_in, const float4* __restrict__ vel_in,
-          float4* __restrict__ pos_out, float4* __restrict__ vel_out,
-          uint32_t* __restrict__ perm, int zbase, uint32_t base, PeerHalo peer) {
+          int G, int zbase, uint32_t base, ReorderIO io, uint32_t* __restrict__ big_cells,
+          uint32_t* __restrict__ big_count, uint32_t big_cap) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const uint32_t id = ids[j];
-    const float4 p = pos_in[id];
-    const float4 v = vel_in[id];
+    const float4 p = io.pos_in[id];
     const uint32_t c = cell_index(p.x, p.y, p.z, bin, G, zbase);
     const uint32_t beg = offsets[c] - base, end = offsets[c + 1] - base;
+    if (end - beg > (uint32_t)kBigCell) {
+        if ((uint32_t)j == beg) {  // one registration per big cell
+            const uint32_t e = atomicAdd(big_count, 1u);
+            if (e < big_cap) big_cells[e] = c;
+        }
+        return;
+    }
     uint32_t rank = 0;
     for (uint32_t k = beg; k < end; k++) rank += (ids[k] < id) ? 1u : 0u;
-    const uint32_t dst = beg + rank;
-    pos_out[dst] = p;
-    vel_out[dst] = v;
-    perm[dst] = id;
-    // halo positions (+ velocities, which do not change before the update) straight into the
-    // neighbours' ghost slots
-    if (peer.pos[0] && dst < peer.n_first) {
-        peer.pos[0][peer.dst[0] + dst] = p;
-        peer.vel[0][peer.dst[0] + dst] = v;
-    }
-    if (peer.pos[1] && dst >= peer.hi_begin) {
-        peer.pos[1][peer.dst[1] + (dst - peer.hi_begin)] = p;
-        peer.vel[1][peer.dst[1] + (dst - peer.hi_begin)] = v;
+    reorder_store(io, beg + rank, id);
+}
+
+// Cells above kBigCell: one block per registered cell sorts the cell's arrival-ordered ID
+// slice ascending (= the stable order) with an LSD radix sort, 8 bits per pass, ping-ponging
+// between ids[] and scratch[] inside the slice, then moves the payload.  Linear in the
+// cell's occupancy per pass, so one cell holding every particle costs O(n), not O(n^2).
+// Each pass: block-wide digit histogram -> exclusive scan -> tiles of kBigThreads IDs in
+// order, each tile ranked stably (match_any inside a warp, a per-digit prefix over the
+// tile's warps) and scattered behind the running digit offsets.
+__global__ void __launch_bounds__(kBigThreads)
+k_reorder_big(uint32_t* __restrict__ ids, uint32_t* __restrict__ scratch,
+              const uint32_t* __restrict__ offsets, uint32_t base, ReorderIO io,
+              const uint32_t* __restrict__ big_cells, const uint32_t* __restrict__ big_count,
+              uint32_t big_cap, int passes) {
+    __shared__ uint32_t s_bin[256];                  // running start of every digit's output range
+    __shared__ uint32_t s_tot[256];
+    __shared__ uint16_t s_warp[kBigThreads / 32][256];  // per-warp digit counts of one tile
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nbig = min(*big_count, big_cap);
+    for (uint32_t e = blockIdx.x; e < nbig; e += gridDim.x) {
+        const uint32_t c = big_cells[e];
+        const uint32_t beg = offsets[c] - base, k = offsets[c + 1] - base - beg;
+        uint32_t* src = ids + beg;
+        uint32_t* dst = scratch + beg;
+        for (int pass = 0; pass < passes; pass++) {
+            const int shift = 8 * pass;
+            if (tid < 256) s_bin[tid] = 0;
+            __syncthreads();
+            for (uint32_t i = tid; i < k; i += kBigThreads)
+                atomicAdd(&s_bin[(src[i] >> shift) & 255u], 1u);
+            __syncthreads();
+            if (warp == 0) {  // exclusive scan of the 256 digit totals: 8 per lane
+                uint32_t v[8], sum = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[q] = s_bin[lane * 8 + q], sum += v[q];
+                uint32_t incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                uint32_t run = incl - sum;
+#pragma unroll
+                for (int q = 0; q < 8; q++) s_bin[lane * 8 + q] = run, run += v[q];
+            }
+            __syncthreads();
+            for (uint32_t t0 = 0; t0 < k; t0 += kBigThreads) {
+                const uint32_t i = t0 + tid;
+                const bool valid = i < k;
+                const uint32_t id = valid ? src[i] : 0u;
+                const uint32_t d = valid ? (id >> shift) & 255u : 0xFFFFFFFFu;
+#pragma unroll
+                for (int q = 0; q < 8; q++) s_warp[warp][lane * 8 + q] = 0;
+                __syncwarp();
+                const unsigned same = __match_any_sync(0xffffffffu, d);
+                const uint32_t in_warp = (uint32_t)__popc(same & ((1u << lane) - 1u));
+                if (valid && in_warp == 0) s_warp[warp][d] = (uint16_t)__popc(same);
+                __syncthreads();
+                if (tid < 256) {  // exclusive prefix over the tile's warps, per digit
+                    uint32_t run = 0;
+                    for (int w = 0; w < kBigThreads / 32; w++) {
+                        const uint32_t x = s_warp[w][tid];
+                        s_warp[w][tid] = (uint16_t)run;
+                        run += x;
+                    }
+                    s_tot[tid] = run;
+                }
+                __syncthreads();
+                if (valid) dst[s_bin[d] + s_warp[warp][d] + in_warp] = id;
+                __syncthreads();
+                if (tid < 256) s_bin[tid] += s_tot[tid];
+            }
+            __syncthreads();  // this pass's global stores are read by the next one
+            uint32_t* t = src;
+            src = dst, dst = t;
+        }
+        for (uint32_t r = tid; r < k; r += kBigThreads) reorder_store(io, beg + r, src[r]);
+        __syncthreads();
     }
 }
 

@@ -33,8 +33,7 @@ def _layer_hist_and_ranges(n, d, spacing, jitter, half, bin_size, grid_res, seed
     return hist
 
 
-def make_rank_scene(n_total, rank, world, seed=0):
-    """-> (scene params, cuts, this rank's particles [m, 8])."""
+def _lattice(n_total):
     radius = scenes.DEFAULT_RADIUS
     size, grid_res = scenes.scaled_box(n_total, radius)
     d = scenes.lattice_side(n_total)
@@ -42,8 +41,20 @@ def make_rank_scene(n_total, rank, world, seed=0):
     jitter = spacing * np.float32(0.5)
     half = jitter / np.float32(2.0)
     bin_size = np.float32(size) / np.float32(grid_res)
+    return radius, size, grid_res, d, spacing, jitter, half, bin_size
+
+
+def slab_layout(n_total, world, seed=0):
+    """-> (global z-layer histogram, equal-count cuts) of the n_total-particle dam break."""
+    radius, size, grid_res, d, spacing, jitter, half, bin_size = _lattice(n_total)
     hist = _layer_hist_and_ranges(n_total, d, spacing, jitter, half, bin_size, grid_res, seed)
-    cuts = slab.slab_cuts(hist, world)
+    return hist, slab.slab_cuts(hist, world)
+
+
+def make_rank_scene(n_total, rank, world, seed=0):
+    """-> (scene params, cuts, this rank's particles [m, 8])."""
+    radius, size, grid_res, d, spacing, jitter, half, bin_size = _lattice(n_total)
+    hist, cuts = slab_layout(n_total, world, seed)
     # lattice planes that can reach this rank's layers (jitter < one plane spacing)
     z_lo, z_hi = cuts[rank] * float(bin_size), cuts[rank + 1] * float(bin_size)
     p_lo = max(int(np.floor(z_lo / float(spacing))) - 1, 0)
@@ -65,6 +76,59 @@ def make_rank_scene(n_total, rank, world, seed=0):
     mine = np.concatenate(out) if out else np.zeros((0, scenes.PARTICLE_FLOATS), np.float32)
     params = dict(grid_res=int(grid_res), size=float(size), particle_radius=float(radius))
     return params, cuts, hist, mine
+
+
+def check_slab_parity(b, one_step, n_total, rank, world, local, stream, steps=2):
+    """Decomposed run == whole-grid run, bit for bit, on real ranks: every rank advances its
+    slab `steps` steps; rank 0 also runs the SAME scene undecomposed on its own GPU; the ranks'
+    buffer 1 (download(1)), concatenated in rank order, must equal the whole-grid buffer 1
+    (slab.py: the concatenation IS the whole-grid state in the whole-grid order).  Collective:
+    every rank calls it.  -> dict for the bench line (raises on a mismatch)."""
+    import torch
+    import torch.distributed as dist
+
+    from . import capi
+
+    for _ in range(steps):
+        one_step()
+    torch.cuda.synchronize()
+    mine = torch.from_numpy(b.download(1)).view(torch.int32).cuda()
+    counts = [None] * world
+    dist.all_gather_object(counts, int(mine.shape[0]))
+    ok = True
+    if rank == 0:
+        sc = scenes.dam_break(n_total, seed=0)
+        with capi.Fluid(num_particles=sc.n, grid_res=sc.grid_res, size=sc.size,
+                        particle_radius=sc.particle_radius, device=local,
+                        stream=stream.cuda_stream) as fl:
+            fl.upload(sc.particles)
+            del sc
+            for _ in range(steps):
+                fl.step(FRAME_DT)
+            whole = torch.from_numpy(fl.download(1)).view(torch.int32)
+        off = 0
+        for r in range(world):
+            ref = whole[off:off + counts[r]].cuda()
+            if r == 0:
+                got = mine
+            else:
+                got = torch.empty((counts[r], 8), dtype=torch.int32, device="cuda")
+                dist.recv(got, src=r)
+            ok = ok and ref.shape == got.shape and bool(torch.equal(ref, got))
+            off += counts[r]
+        ok = ok and off == whole.shape[0] == n_total
+        del whole
+    else:
+        dist.send(mine, dst=0)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    if not int(flag.item()):
+        raise RuntimeError("slab parity FAILED: the decomposed run differs from the whole-grid run")
+    return {"status": "bit-exact", "steps": steps, "particles": int(n_total),
+            "against": "whole-grid run of the same scene on rank 0's GPU; ranks' buffer 1 "
+                       "concatenated in rank order, compared as raw 32-bit words"}
 
 
 def run(args, rank, world, local):
@@ -90,6 +154,7 @@ def run(args, rank, world, local):
                              ghost_capacity=ghost_cap, migrant_capacity=mig_cap, device=local,
                              flags=flags, stream=stream.cuda_stream)
     b.upload(mine)
+    del mine
     drv = slab.SlabDriver(b, rank, world)
     peer = args.exchange == "peer"
     if peer:
@@ -104,6 +169,10 @@ def run(args, rank, world, local):
     def barrier():
         dist.barrier()
         torch.cuda.synchronize()
+
+    parity = None
+    if not args.no_slab_parity:
+        parity = check_slab_parity(b, one_step, n_total, rank, world, local, stream)
 
     warmup = max(args.warmup, 3)
     for _ in range(warmup):
@@ -121,7 +190,7 @@ def run(args, rank, world, local):
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):   # no per-step sync: the host runs ahead like a real frame loop
-        one_step()                # (the only host wait is the step's own particle-count read)
+        one_step()
     e1.record(stream)
     barrier()
     t_wall1 = time.time()
@@ -129,6 +198,7 @@ def run(args, rank, world, local):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)       # device time, max over ranks
     ms_per_step = float(ms.item()) / args.steps
     launches = b.fluid.launch_count() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1)
     # stage split from a few extra steps (reading the stage events syncs, so not in the timed loop)
     n_stage = max(1, min(3, args.steps))
     for _ in range(n_stage):
@@ -141,7 +211,9 @@ def run(args, rank, world, local):
     assert int(n_now.item()) == n_total, (int(n_now.item()), n_total)  # nothing lost in migration
     value = n_total / (ms_per_step * 1e-3)
 
-    # ---- e2e: every rank's slab goes host -> device and back every step
+    # ---- e2e: every rank's slab goes host -> device and back every step, through ONE C-ABI
+    # call per step (wc_slab_step_peer_host: H2D of the pinned input, the step, and the result
+    # stored into the pinned output by the update kernel itself)
     e2e = None
     if not args.no_e2e:
         cur = b.download(1)
@@ -149,18 +221,26 @@ def run(args, rank, world, local):
         h_out = torch.empty((cap, 8), dtype=torch.float32, pin_memory=True)
         n_cur = cur.shape[0]
         h_in[:n_cur].copy_(torch.from_numpy(cur))
+        del cur
         steps_e = max(3, min(args.steps, 10))
         h2d = d2h = 0
+        fused = peer and hasattr(b.fluid, "slab_step_peer_host")
         barrier()
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
         for _ in range(steps_e):
-            b.fluid.upload((h_in.data_ptr(), n_cur))
-            h2d += n_cur * 32
-            one_step()
-            n_cur = b.num_particles
-            b.fluid.download(1, out=(h_out.data_ptr(), n_cur))
+            if fused:
+                info = b.fluid.slab_step_peer_host((h_in.data_ptr(), n_cur), h_out.data_ptr(), cap,
+                                                   FRAME_DT)
+                h2d += n_cur * 32
+                n_cur = info["n_owned"]
+            else:
+                b.fluid.upload((h_in.data_ptr(), n_cur))
+                h2d += n_cur * 32
+                one_step()
+                n_cur = b.num_particles
+                b.fluid.download(1, out=(h_out.data_ptr(), n_cur))
             d2h += n_cur * 32
             h_in, h_out = h_out, h_in
         ev1.record(stream)
@@ -172,8 +252,11 @@ def run(args, rank, world, local):
         ms_e_step = float(ms_e.item()) / steps_e
         e2e = {"value": n_total / (ms_e_step * 1e-3), "unit": bench.UNIT, "ms_per_step": ms_e_step,
                "h2d_bytes_per_step": int(tot[0].item()) // steps_e,
-               "d2h_bytes_per_step": int(tot[1].item()) // steps_e}
-    clocks = sampler.stop(t_wall0, t_wall1)
+               "d2h_bytes_per_step": int(tot[1].item()) // steps_e,
+               "api": "wc_slab_step_peer_host per rank (pinned host AoS in and out; D2H fused into "
+                      "the update kernel)" if fused else
+                      "wc_upload_particles + slab step + wc_download_particles per rank"}
+        del h_in, h_out
 
     per_stage = {k: v / n_stage for k, v in stage_ms.items()}
     stage_t = torch.tensor([per_stage[k] for k in capi.STAGES], device="cuda")
@@ -181,28 +264,34 @@ def run(args, rank, world, local):
     per_stage = dict(zip(capi.STAGES, [float(x) for x in stage_t.tolist()]))
     counts = [None] * world
     dist.all_gather_object(counts, int(b.num_particles))
+    b.close()
+    torch.cuda.empty_cache()
+
+    # ---- the same per-GPU load on ONE GPU, whole grid, in this very run: the denominator of
+    # the weak-scaling efficiency (the N = 1 bench line is the 1M scene, another load)
+    weak = None
+    if rank == 0 and not args.no_weak_baseline:
+        ppg = n_total // world
+        wb = bench.measure_single_gpu(args, scenes.dam_break(ppg, seed=0), min(args.steps, 20), 3,
+                                      local, with_e2e=False, sample_clocks=False)
+        weak = {"particles": wb["particles"], "ms_per_step": wb["ms_per_step"],
+                "value": wb["value"], "unit": bench.UNIT, "steps": wb["steps"],
+                "stage_ms": wb["stage_ms"],
+                "what": f"whole-grid dam break of {ppg} particles on rank 0's GPU alone, after "
+                        f"the {world}-GPU run"}
     if rank == 0:
         peak, peak_src = bench.peak_hbm()
         dom = max(per_stage, key=per_stage.get)
         n_rank_max = max(counts)
         achieved = bench.ALGO_BYTES[dom] * n_rank_max / (per_stage[dom] * 1e-3) / 1e9
         step_gbs = bench.ALGO_BYTES_STEP * n_total / world / (ms_per_step * 1e-3) / 1e9
-
-        class _Sc:  # what bench.workload_config reads
-            size, grid_res, particle_radius = params["size"], params["grid_res"], params["particle_radius"]
-
         line = {
             "metric": bench.METRIC, "value": value, "unit": bench.UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": bench.workload_config(args, _Sc, n_total, world, {
-                "l2": "per-rank working set > L2, no flush", "kernels": "tiled",
-                "slab_cuts": [int(c) for c in cuts], "particles_per_rank": counts,
-                "exchange": ("peer memory (CUDA IPC over NVLink): copies into the neighbour's "
-                             "buffers + device-side signals" if peer else "NCCL P2P") +
-                            " with slab neighbours: layer counts, halo positions, "
-                            "halo rho/P/velocity, migrants"}),
+            "config": bench.arm_config(args, world, (hist, cuts)),
+            "particles_per_rank_end": counts,
             "stage_ms": per_stage,
             "roofline": {"bound": "hbm", "kernel": bench.KERNEL_NAMES[dom], "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -213,7 +302,14 @@ def run(args, rank, world, local):
             "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
                               "frac": step_gbs / peak, "note": "per GPU, whole step incl. exchange"},
             "clocks": clocks, "gpu_launches": int(launches) * world,
+            "gpu_launches_per_step_per_rank": int(launches) / max(args.steps, 1),
         }
+        if parity:
+            line["slab_parity"] = parity["status"]
+            line["slab_parity_detail"] = parity
+        if weak:
+            line[f"weak_baseline_{weak['particles'] // 1_000_000}m"] = weak
+            line["efficiency_vs_weak_baseline"] = value / (world * weak["value"])
         if e2e:
             line["e2e"] = e2e
         print(json.dumps(line), flush=True)
