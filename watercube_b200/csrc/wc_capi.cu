@@ -345,20 +345,22 @@ int sort_reorder_phase(wc_handle* h, bool timed, int n_in, int n_sorted) {
             h->ids, h->offsets, n_sorted, bin, G, h->zbase, (uint32_t)h->Cg, io, h->big_cells,
             h->big_count, (uint32_t)h->big_cap);
         WC_CHECK_LAUNCH(h);
-        // cells above kBigCell particles (none in a physical scene: the kernel then exits at
-        // once): radix-sorted per cell; IDs index the (virtual) input, hence the pass count
-        int bits = 1;
-        while (bits < 32 && (1ll << bits) < (long long)n_in) bits++;
-        k_reorder_big<<<kBigBlocks, kBigThreads, 0, h->stream>>>(
-            h->ids, h->ranks, h->offsets, (uint32_t)h->Cg, io, h->big_cells, h->big_count,
-            (uint32_t)h->big_cap, (bits + 7) / 8);
-        WC_CHECK_LAUNCH(h);
     }
-    if (h->groups) {  // cut the owned rows into <= 32-particle groups for the gathers
+    {   // group table for the gathers + the cells above kBigCell particles, one launch
         const int row0 = h->slab ? G : 0, row1 = h->slab ? (h->Lz - 1) * G : h->Lz * G;
-        k_build_groups<<<div_up(row1 - row0, kGroupRows), kGroupRows, 0, h->stream>>>(
-            h->offsets, G, row0, row1, h->groups, h->num_groups);
-        WC_CHECK_LAUNCH(h);
+        const bool moved = n_in > 0 && n_sorted > 0;
+        const ReorderIO io{h->pos[0], h->vel[0], h->pos[1] + h->Cg, h->vel[1] + h->Cg, h->perm,
+                           h->slab ? peer_halo(h) : PeerHalo()};
+        int bits = 1;  // IDs index the (virtual) input: that many radix passes
+        while (bits < 32 && (1ll << bits) < (long long)n_in) bits++;
+        if (h->groups || moved) {
+            k_finish_sort<<<finish_sort_blocks(h->groups ? row1 - row0 : 0), kBigThreads, 0,
+                            h->stream>>>(h->offsets, G, row0, row1, h->groups, h->num_groups,
+                                         moved ? h->ids : nullptr, h->ranks, (uint32_t)h->Cg, io,
+                                         h->big_cells, h->big_count, (uint32_t)h->big_cap,
+                                         (bits + 7) / 8);
+            WC_CHECK_LAUNCH(h);
+        }
     }
     if (timed && (rc = record(h, 3))) return rc;
     h->sorted_valid = true;
@@ -840,8 +842,12 @@ int wc_sort_only(wc_handle* h) {
     if (!h) return fail(WC_ERR_INVALID, "handle is NULL");
     if (h->slab) return fail(WC_ERR_INVALID, "slab handle: use the wc_slab_* sequence");
     WC_CUDA(cudaSetDevice(h->p.device));
-    h->have_times = false;
-    return run_sort(h, false);
+    // with WC_FLAG_STAGE_TIMING the three sort stages are timed (density / update read as 0)
+    int rc = run_sort(h, true);
+    if (rc) return rc;
+    if ((rc = record(h, 4)) || (rc = record(h, 5))) return rc;
+    h->have_times = (h->p.flags & WC_FLAG_STAGE_TIMING) != 0;
+    return WC_OK;
 }
 
 int wc_density_only(wc_handle* h, const wc_step_params* sp) {

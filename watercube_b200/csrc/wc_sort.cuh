@@ -193,10 +193,10 @@ k_scatter_ids(const uint32_t* __restrict__ cell_ids, const uint32_t* __restrict_
 // The in-cell count is quadratic in the cell's occupancy, which is fine at the reference's
 // ~20 particles per cell; a cell holding more than kBigCell particles (all particles piled
 // into a few cells, NaN positions collapsing into cell 0, gridRes of 1..few) is only
-// registered here and handled by k_reorder_big.
+// registered here and handled by reorder_big_cells (k_finish_sort).
 constexpr int kBigCell = 256;
 constexpr int kBigThreads = 1024;
-constexpr int kBigBlocks = 296;  // 2 x 148 SMs; blocks stride over the registered cells
+constexpr int kBigBlocks = 148;  // blocks stride over the registered cells
 
 struct ReorderIO {
     const float4* pos_in;
@@ -207,9 +207,8 @@ struct ReorderIO {
     PeerHalo peer;
 };
 
-__device__ __forceinline__ void reorder_store(const ReorderIO& io, uint32_t dst, uint32_t id) {
-    const float4 p = io.pos_in[id];
-    const float4 v = io.vel_in[id];
+__device__ __forceinline__ void reorder_store(const ReorderIO& io, uint32_t dst, uint32_t id,
+                                              float4 p, float4 v) {
     io.pos_out[dst] = p;
     io.vel_out[dst] = v;
     io.perm[dst] = id;
@@ -233,6 +232,7 @@ k_reorder(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ offsets
     if (j >= n) return;
     const uint32_t id = ids[j];
     const float4 p = io.pos_in[id];
+    const float4 v = io.vel_in[id];  // in flight under the rank loop
     const uint32_t c = cell_index(p.x, p.y, p.z, bin, G, zbase);
     const uint32_t beg = offsets[c] - base, end = offsets[c + 1] - base;
     if (end - beg > (uint32_t)kBigCell) {
@@ -244,22 +244,25 @@ k_reorder(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ offsets
     }
     uint32_t rank = 0;
     for (uint32_t k = beg; k < end; k++) rank += (ids[k] < id) ? 1u : 0u;
-    reorder_store(io, beg + rank, id);
+    reorder_store(io, beg + rank, id, p, v);
 }
 
-// Cells above kBigCell: one block per registered cell sorts the cell's arrival-ordered ID
-// slice ascending (= the stable order) with an LSD radix sort, 8 bits per pass, ping-ponging
-// between ids[] and scratch[] inside the slice, then moves the payload.  Linear in the
-// cell's occupancy per pass, so one cell holding every particle costs O(n), not O(n^2).
-// Each pass: block-wide digit histogram -> exclusive scan -> tiles of kBigThreads IDs in
-// order, each tile ranked stably (match_any inside a warp, a per-digit prefix over the
-// tile's warps) and scattered behind the running digit offsets.
-__global__ void __launch_bounds__(kBigThreads)
-k_reorder_big(uint32_t* __restrict__ ids, uint32_t* __restrict__ scratch,
-              const uint32_t* __restrict__ offsets, uint32_t base, ReorderIO io,
-              const uint32_t* __restrict__ big_cells, const uint32_t* __restrict__ big_count,
-              uint32_t big_cap, int passes) {
+// Cells above kBigCell (second part of k_finish_sort): one block per registered cell sorts
+// the cell's arrival-ordered ID slice ascending (= the stable order) with an LSD radix sort,
+// 8 bits per pass, ping-ponging between ids[] and scratch[] inside the slice; the last pass
+// moves the payload instead of storing the ID.  Linear in the cell's occupancy per pass, so one
+// cell holding every particle costs O(n), not O(n^2).
+// Each pass walks the slice in tiles of kBigThreads IDs, in order: a tile is ranked stably
+// (match_any inside a warp, a per-digit prefix over the tile's warps) and scattered behind the
+// running digit offsets.  The digit histogram of pass p + 1 is taken while pass p scatters, and
+// a tile's IDs are loaded one tile ahead.
+__device__ __forceinline__ void
+reorder_big_cells(uint32_t* __restrict__ ids, uint32_t* __restrict__ scratch,
+                  const uint32_t* __restrict__ offsets, uint32_t base, const ReorderIO& io,
+                  const uint32_t* __restrict__ big_cells, const uint32_t* __restrict__ big_count,
+                  uint32_t big_cap, int passes) {
     __shared__ uint32_t s_bin[256];                  // running start of every digit's output range
+    __shared__ uint32_t s_next[256];                 // histogram of the next pass's digit
     __shared__ uint32_t s_tot[256];
     __shared__ uint16_t s_warp[kBigThreads / 32][256];  // per-warp digit counts of one tile
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -269,17 +272,17 @@ k_reorder_big(uint32_t* __restrict__ ids, uint32_t* __restrict__ scratch,
         const uint32_t beg = offsets[c] - base, k = offsets[c + 1] - base - beg;
         uint32_t* src = ids + beg;
         uint32_t* dst = scratch + beg;
+        if (tid < 256) s_next[tid] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < k; i += kBigThreads) atomicAdd(&s_next[src[i] & 255u], 1u);
+        __syncthreads();
         for (int pass = 0; pass < passes; pass++) {
             const int shift = 8 * pass;
-            if (tid < 256) s_bin[tid] = 0;
-            __syncthreads();
-            for (uint32_t i = tid; i < k; i += kBigThreads)
-                atomicAdd(&s_bin[(src[i] >> shift) & 255u], 1u);
-            __syncthreads();
+            const bool last = pass + 1 == passes;
             if (warp == 0) {  // exclusive scan of the 256 digit totals: 8 per lane
                 uint32_t v[8], sum = 0;
 #pragma unroll
-                for (int q = 0; q < 8; q++) v[q] = s_bin[lane * 8 + q], sum += v[q];
+                for (int q = 0; q < 8; q++) v[q] = s_next[lane * 8 + q], sum += v[q];
                 uint32_t incl = sum;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -291,10 +294,14 @@ k_reorder_big(uint32_t* __restrict__ ids, uint32_t* __restrict__ scratch,
                 for (int q = 0; q < 8; q++) s_bin[lane * 8 + q] = run, run += v[q];
             }
             __syncthreads();
+            if (tid < 256) s_next[tid] = 0;
+            uint32_t id_next = tid < k ? src[tid] : 0u;
+            __syncthreads();
             for (uint32_t t0 = 0; t0 < k; t0 += kBigThreads) {
                 const uint32_t i = t0 + tid;
                 const bool valid = i < k;
-                const uint32_t id = valid ? src[i] : 0u;
+                const uint32_t id = id_next;
+                if (i + kBigThreads < k) id_next = src[i + kBigThreads];  // one tile ahead
                 const uint32_t d = valid ? (id >> shift) & 255u : 0xFFFFFFFFu;
 #pragma unroll
                 for (int q = 0; q < 8; q++) s_warp[warp][lane * 8 + q] = 0;
@@ -302,9 +309,11 @@ k_reorder_big(uint32_t* __restrict__ ids, uint32_t* __restrict__ scratch,
                 const unsigned same = __match_any_sync(0xffffffffu, d);
                 const uint32_t in_warp = (uint32_t)__popc(same & ((1u << lane) - 1u));
                 if (valid && in_warp == 0) s_warp[warp][d] = (uint16_t)__popc(same);
+                if (valid && !last) atomicAdd(&s_next[(id >> (shift + 8)) & 255u], 1u);
                 __syncthreads();
                 if (tid < 256) {  // exclusive prefix over the tile's warps, per digit
                     uint32_t run = 0;
+#pragma unroll 8
                     for (int w = 0; w < kBigThreads / 32; w++) {
                         const uint32_t x = s_warp[w][tid];
                         s_warp[w][tid] = (uint16_t)run;
@@ -313,7 +322,11 @@ k_reorder_big(uint32_t* __restrict__ ids, uint32_t* __restrict__ scratch,
                     s_tot[tid] = run;
                 }
                 __syncthreads();
-                if (valid) dst[s_bin[d] + s_warp[warp][d] + in_warp] = id;
+                if (valid) {
+                    const uint32_t at = s_bin[d] + s_warp[warp][d] + in_warp;
+                    if (last) reorder_store(io, beg + at, id, io.pos_in[id], io.vel_in[id]);
+                    else dst[at] = id;
+                }
                 __syncthreads();
                 if (tid < 256) s_bin[tid] += s_tot[tid];
             }
@@ -321,8 +334,6 @@ k_reorder_big(uint32_t* __restrict__ ids, uint32_t* __restrict__ scratch,
             uint32_t* t = src;
             src = dst, dst = t;
         }
-        for (uint32_t r = tid; r < k; r += kBigThreads) reorder_store(io, beg + r, src[r]);
-        __syncthreads();
     }
 }
 

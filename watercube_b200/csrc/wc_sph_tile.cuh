@@ -26,6 +26,7 @@
 #pragma once
 
 #include "wc_common.cuh"
+#include "wc_sort.cuh"
 #include "wc_sph_v1.cuh"
 
 namespace wc {
@@ -64,6 +65,18 @@ constexpr int kDensityWarps = WC_DENSITY_WARPS;  // warps (= groups) per block, 
 #ifndef WC_DROP_SELF
 #define WC_DROP_SELF 1
 #endif
+// 1: the cull walks the nine slices as one sequence of 32-candidate chunks (see gather_group).
+#ifndef WC_CULL_CHUNKS
+#define WC_CULL_CHUNKS 0
+#endif
+// 1: the walk prefers bits whose stage slot lies in the lane's own bank group (see walk()).
+#ifndef WC_PICK_BANKS
+#define WC_PICK_BANKS 0
+#endif
+// 1: list candidates that no target of the group accepted as padding slots.
+#ifndef WC_LIST_DROP_UNUSED
+#define WC_LIST_DROP_UNUSED 1
+#endif
 constexpr int kUpdateWarps = WC_UPDATE_WARPS;  // warps per block, update pass (6 KB stage each)
 constexpr int kChunk = 128;                // staged candidates per density batch (4 words)
 constexpr int kCullDepth = 4;              // density pass: cull loads in flight per lane
@@ -85,10 +98,11 @@ constexpr uint32_t kListOverflow = 0xFFFFFFFFu;  // nbr_words value: list did no
 // numbering is arbitrary between blocks -- nothing depends on it: a group's number only
 // selects its slice of the neighbour list, which the density and update passes of the same
 // step share.  Rows [row_begin, row_end) are covered (slab mode skips the two ghost layers).
-constexpr int kGroupRows = 128;
-__global__ void __launch_bounds__(kGroupRows)
-k_build_groups(const uint32_t* __restrict__ offsets, int G, int row_begin, int row_end,
-               uint4* __restrict__ groups, uint32_t* __restrict__ num_groups) {
+constexpr int kGroupRows = 1024;  // = kBigThreads: the table is built by k_finish_sort's blocks
+__device__ __forceinline__ void build_groups_block(const uint32_t* __restrict__ offsets, int G,
+                                                   int row_begin, int row_end,
+                                                   uint4* __restrict__ groups,
+                                                   uint32_t* __restrict__ num_groups) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -131,6 +145,26 @@ k_build_groups(const uint32_t* __restrict__ offsets, int G, int row_begin, int r
             groups[g_src + k] = make_uint4(b_src + 32u * k, (uint32_t)(r0 + warp * 32 + src),
                                            min(32u, n_src - 32u * k), 0u);
     }
+}
+
+// Last kernel of the sort: the blocks first cut their share of the (y,z) rows into groups,
+// then sort and move the cells above kBigCell particles that k_reorder registered (none in a
+// physical scene).  One launch for both, because the second part is almost always empty.
+__global__ void __launch_bounds__(kBigThreads)
+k_finish_sort(const uint32_t* __restrict__ offsets, int G, int row_begin, int row_end,
+              uint4* __restrict__ groups, uint32_t* __restrict__ num_groups,
+              uint32_t* __restrict__ ids, uint32_t* __restrict__ scratch, uint32_t base,
+              ReorderIO io, const uint32_t* __restrict__ big_cells,
+              const uint32_t* __restrict__ big_count, uint32_t big_cap, int passes) {
+    static_assert(kGroupRows == kBigThreads, "one block shape for both parts");
+    if (groups && row_begin + (int)blockIdx.x * kGroupRows < row_end)
+        build_groups_block(offsets, G, row_begin, row_end, groups, num_groups);
+    if (ids) reorder_big_cells(ids, scratch, offsets, base, io, big_cells, big_count, big_cap, passes);
+}
+
+inline int finish_sort_blocks(int rows) {
+    const int for_groups = (rows + kGroupRows - 1) / kGroupRows;
+    return for_groups > kBigBlocks ? for_groups : kBigBlocks;
 }
 
 // Upper bound of the number of groups for n particles in `rows` rows.
@@ -313,7 +347,15 @@ struct DensityAcc {
             if (kDebug) nn += (uint32_t)__popc(mk);
             if (idx_out) {
                 if (words_used < (uint32_t)cap_words) {
+#if WC_LIST_DROP_UNUSED
+                    // a staged candidate no target accepted (a third of them: the cull keeps the
+                    // box of the targets grown by h) is listed as a padding slot, so the update
+                    // pass does not fetch it
+                    const unsigned any = __reduce_or_sync(0xffffffffu, mk);
+                    idx_out[(size_t)words_used * 32] = ((any >> lane) & 1u) ? st.j[k0 + lane] : kNoIndex;
+#else
                     idx_out[(size_t)words_used * 32] = st.j[k0 + lane];
+#endif
                     mask_out[(size_t)words_used * 32] = mk;
                 } else {
                     overflow = true;
@@ -375,6 +417,14 @@ struct UpdateAcc {
         mptr = (nwb > 2) ? mptr + 256u : mend;
         const float4* abase = st.a;  // slot 0 of the word being drained
         float4 qa0 = make_float4(0, 0, 0, 0), qb0 = qa0, qa1 = qa0, qb1 = qa0;
+#if WC_PICK_BANKS
+        // A pick is two per-lane LDS.128: the eight lanes of a quarter-warp are served together
+        // and collide when two of them hit the same 16-byte bank group (slot index mod 8 = bit
+        // index mod 8) at different slots.  Every lane therefore prefers, among the bits left in
+        // its word, one whose bank group is (lane + pick number) mod 8 -- distinct within the
+        // quarter-warp -- and only falls back to the highest bit when it has none there.
+        unsigned pat = 0x01010101u << (lane & 7);
+#endif
         auto pick = [&](float4& qa, float4& qb) -> bool {
             if (m == 0u) {
                 m = mn;
@@ -383,7 +433,13 @@ struct UpdateAcc {
                 mptr = (mptr == mend) ? mend : mptr + 128u;
             }
             const bool on = m != 0u;
+#if WC_PICK_BANKS
+            const unsigned pref = m & pat;
+            pat = __funnelshift_l(pat, pat, 1);
+            const unsigned hb = highest_bit(pref ? pref : m);
+#else
             const unsigned hb = highest_bit(m);  // 0xffffffff when no bit is left
+#endif
             if (on) {
                 const float4* q = abase + hb;
                 qa = q[0];
@@ -391,7 +447,11 @@ struct UpdateAcc {
             } else {
                 qa.w = 0.0f;  // see pair()
             }
+#if WC_PICK_BANKS
+            m &= ~(on ? (1u << hb) : 0u);
+#else
             m &= bits_below(hb);  // drops bit hb (m stays 0 when it was 0)
+#endif
             return on;
         };
         while (__any_sync(0xffffffffu, (m | mn) != 0u || mptr != mend)) {
@@ -586,6 +646,62 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
     }
     constexpr int kDepth = Stage::kDepth;
     int cnt = 0, head = 0;  // pending candidates are stage[head, head + cnt) (mod ring)
+#if WC_CULL_CHUNKS
+    // The nine slices are walked as ONE sequence of 32-candidate chunks (warp-uniform cursor:
+    // slice number, position, end), kDepth chunks in flight per lane, so a slice costs
+    // ceil(len / 32) cull steps and never a mostly-empty kDepth x 32 block of its own.
+    int sl = -1;
+    uint32_t cur = 0, cend = 0;
+    for (bool more = true; more;) {
+        uint32_t cb[kDepth], ce[kDepth];
+#pragma unroll
+        for (int k = 0; k < kDepth; k++) {
+            while (cur >= cend && sl < 9) {
+                sl++;
+                cur = __shfl_sync(full, sbeg, sl & 15);
+                cend = sl < 9 ? __shfl_sync(full, send, sl & 15) : 0u;
+            }
+            if (sl >= 9) {
+                cb[k] = ce[k] = 0u;  // no chunk: every lane fails the index test
+                more = false;
+            } else {
+                cb[k] = cur, ce[k] = cend;
+                cur += 32u;
+            }
+        }
+        // The loads are unconditional: a slice's last chunk reads up to 31 entries past its
+        // end (the arrays carry kCullOverread slack); those lanes fail the index test.
+        float4 q[kDepth];
+#pragma unroll
+        for (int k = 0; k < kDepth; k++) q[k] = pos_rho[cb[k] + lane];
+#pragma unroll
+        for (int k = 0; k < kDepth; k++) {
+            const uint32_t j = cb[k] + lane;
+            const float ex = fmaxf(fmaxf(bx0 - q[k].x, q[k].x - bx1), 0.0f);
+            const float ey = fmaxf(fmaxf(by0 - q[k].y, q[k].y - by1), 0.0f);
+            const float ez = fmaxf(fmaxf(bz0 - q[k].z, q[k].z - bz1), 0.0f);
+            const bool keep = j < ce[k] && ex * ex + ey * ey + ez * ez < Tcull;
+            const unsigned km = __ballot_sync(full, keep);
+            if (keep) {
+                const int at = cnt + __popc(km & lt);
+                st.put(Stage::kWrap ? ((head + at) & Stage::kWrap) : at, q[k], j, vel_pres);
+            }
+            cnt += __popc(km);
+        }
+        if (cnt >= Stage::kBatch) {
+            __syncwarp();
+            acc.process(st, head, Stage::kBatch, c, p, v, Teff);
+            __syncwarp();
+            cnt -= Stage::kBatch;
+            if constexpr (Stage::kWrap != 0) {
+                head ^= Stage::kBatch;  // the ring's other half
+            } else if (cnt > 0) {  // linear stage: move the (< 32) leftovers to the front
+                st.move(lane, Stage::kBatch + lane, lane < cnt);
+                __syncwarp();
+            }
+        }
+    }
+#else
     for (int s = 0; s < 9; s++) {
         const uint32_t end = __shfl_sync(full, send, s);
         for (uint32_t j0 = __shfl_sync(full, sbeg, s); j0 < end; j0 += 32 * kDepth) {
@@ -626,6 +742,7 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
             }
         }
     }
+#endif
     if (cnt > 0) {  // final partial batch: pad to a multiple of 32
         const int count = (cnt + 31) & ~31;
         if (cnt + lane < count) st.pad(head + cnt + lane);
