@@ -137,6 +137,8 @@ int wc_default_params(wc_params* p);
 int wc_default_step_params(wc_step_params* sp);
 /* Fluid::setup constants without touching a device (Fluid.cpp:206-216). */
 int wc_derive(const wc_params* p, wc_derived* d);
+/* Number of CUDA devices this process sees (0 and WC_ERR_NO_DEVICE without a driver). */
+int wc_device_count(int32_t* count);
 
 /* Fluid::setup (Fluid.cpp:203-235) + Sort::prepareBuffers (Sort.cpp:67-94): allocate the
  * two particle buffers, count/offset/sorted buffers and scratch on p->device. */
@@ -163,6 +165,13 @@ int wc_step(wc_handle* h, float frame_dt, const wc_step_params* sp);
  * complete on return. */
 int wc_step_host(wc_handle* h, float frame_dt, const wc_step_params* sp,
                  const wc_particle* host_in, int32_t n, wc_particle* host_out);
+/* The same step with the new buffer 1 ALSO written, by the update kernel itself, as the
+ * reference's 32-byte AoS Particle records (util.h:29-35) into aos_dst: a device pointer --
+ * e.g. the SSBO Fluid::renderParticles binds at index 0 (Fluid.cpp:389-406,
+ * assets/fluid/particle.vert:19-31), registered with cudaGraphicsGLRegisterBuffer and mapped
+ * -- or page-locked mapped host memory.  num_particles * 32 bytes, cell-sorted order.  No pack
+ * kernel, no extra pass over the state.  Asynchronous on the handle's stream. */
+int wc_step_export(wc_handle* h, float frame_dt, const wc_step_params* sp, void* aos_dst);
 /* Stage-level entry points, like the reference's separate runXProg methods. */
 int wc_sort_only(wc_handle* h);                                      /* Sort::run, Sort.cpp:254 */
 int wc_density_only(wc_handle* h, const wc_step_params* sp);         /* Fluid.cpp:268 */
@@ -197,7 +206,8 @@ int wc_sync(wc_handle* h);
  * buffers must be zero-filled (wc_slab_clear_recv).
  *   wc_slab_sort_count   unpack mig_in, hash + count + scan of the owned layers
  *     exchange lc_send[d] -> neighbour's lc_recv[1-d]              (lc_bytes each)
- *   wc_slab_sync_info    host sync; returns the particle counts of this step
+ *   wc_slab_sync_info    host sync; returns the particle counts of this step (a host-driven
+ *                        transport needs them to size the halo messages; optional otherwise)
  *   wc_slab_reorder      ghost-layer offsets + stable reorder of the owned particles
  *     exchange halo positions: first / last owned layer of buffer 2 -> neighbour's ghost slots
  *   wc_slab_density
@@ -252,10 +262,24 @@ typedef struct wc_slab_ipc {
 } wc_slab_ipc;
 int wc_slab_ipc_export(wc_handle* h, wc_slab_ipc* out);
 /* One whole step of a slab handle whose neighbours are all attached (or absent): the five
- * phase calls above in one, so the host touches the step once; its only wait is the read of
- * this step's particle counts (info as in wc_slab_sync_info, may be NULL).  A non-zero error
- * count (capacity overflow, lost migrants) returns WC_ERR_CAPACITY. */
+ * phase calls above in one.  Nothing in the step depends on a host read-back -- the step's
+ * counts live in a device record, every launch is sized by capacity, waits and signals sit
+ * inside the consuming / producing kernels -- so with info == NULL the call only queues the
+ * step (eleven kernels) and returns; one host thread can then drive every GPU of the box
+ * (core::Fluid::devices, wc_headless --gpus N) and run steps ahead.  With info != NULL it
+ * waits for the step and reports its counts (as wc_slab_sync_info); a non-zero error word
+ * (capacity overflow, lost migrants, a neighbour's signal missing) returns WC_ERR_CAPACITY.
+ * Errors are sticky on the device: an asynchronous caller meets them at its next info read,
+ * download or wc_device_ptrs. */
 int wc_slab_step_peer(wc_handle* h, float frame_dt, const wc_step_params* sp, int32_t info[8]);
+/* wc_step_host for a slab handle (util::setParticles -> update -> util::getParticles as one
+ * call per rank): uploads n particles from host_in (NULL: step the resident state), steps, and
+ * leaves the slab's new buffer 1 in host_out (room for out_capacity >= `capacity` particles;
+ * info[0] of them are valid).  Page-locked host_out: the update kernel stores the records into
+ * it directly.  Synchronous; info must not be NULL. */
+int wc_slab_step_peer_host(wc_handle* h, float frame_dt, const wc_step_params* sp,
+                           const wc_particle* host_in, int32_t n, wc_particle* host_out,
+                           int32_t out_capacity, int32_t info[8]);
 int wc_slab_peer_open(wc_handle* h, int32_t direction, const wc_slab_ipc* peer);
 int wc_slab_peer_attach(wc_handle* h, int32_t direction, wc_handle* peer);
 

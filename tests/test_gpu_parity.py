@@ -349,6 +349,48 @@ def test_step_host_equals_upload_step_download(capi, pinned, simple):
         np.testing.assert_array_equal(b.numpy(), ref[2])
 
 
+@pytest.mark.parametrize("simple", [False, True], ids=["tiled", "simple"])
+def test_interop_exports_into_foreign_device_buffers(capi, simple):
+    """SURVEY.md 8(f) row 1, the renderer's side of the boundary (Fluid::renderParticles binds
+    buffer 1 as an SSBO of 32-byte AoS Particle records, Fluid.cpp:389-406 /
+    particle.vert:19-31): a device buffer the library does not own -- here a torch tensor,
+    in the app a mapped cudaGraphicsGLRegisterBuffer SSBO -- receives the records either from
+    the pack kernel (wc_export_aos_device, buffers 1 and 2) or from the update kernel itself
+    (wc_step_export, no pack pass), bit-identical to what wc_download_particles returns."""
+    import torch
+
+    sc = scenes.dam_break(70000, seed=29)
+    flags = capi.FLAG_SIMPLE_KERNELS if simple else 0
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ssbo = torch.full((sc.n + 16, 8), float("nan"), dtype=torch.float32, device="cuda")
+        with capi.Fluid(num_particles=sc.n, grid_res=sc.grid_res, size=sc.size,
+                        particle_radius=sc.particle_radius, flags=flags,
+                        stream=stream.cuda_stream) as fl:
+            fl.upload(sc.particles)
+            fl.step(FRAME_DT)
+            for which in (1, 2):
+                ssbo.fill_(float("nan"))
+                fl.export_aos_device(which, ssbo.data_ptr())
+                stream.synchronize()
+                got = ssbo.cpu().numpy()
+                np.testing.assert_array_equal(got[:sc.n], fl.download(which))
+                assert np.isnan(got[sc.n:]).all()                  # nothing past n * 32 bytes
+            ssbo.fill_(float("nan"))
+            fl.step_export(ssbo.data_ptr(), FRAME_DT)              # the step fills the SSBO itself
+            stream.synchronize()
+            got = ssbo.cpu().numpy()
+            np.testing.assert_array_equal(got[:sc.n], fl.download(1))
+            assert np.isnan(got[sc.n:]).all()
+            with pytest.raises(capi.WcError):
+                fl.step_export(np.zeros((sc.n, 8), f32).ctypes.data, FRAME_DT)  # pageable host
+    with gpu_fluid(capi, sc, flags) as fl:                         # and it is the plain step
+        fl.upload(sc.particles)
+        fl.step(FRAME_DT)
+        fl.step(FRAME_DT)
+        np.testing.assert_array_equal(fl.download(1), got[:sc.n])
+
+
 def test_simple_and_tiled_kernels_agree_bitwise_on_integers(capi):
     sc = scenes.dam_break(120000, seed=13)
     res = [run_gpu_stages(capi, sc, simple) for simple in (False, True)]

@@ -113,13 +113,21 @@ int main(int argc, char** argv) {
     ps[1].position = vec3(1, 2, 3); ps[2].pressure = 7.5f;
     util::CheckpointHeader h = util::CheckpointHeader();
     h.grid_res = 21; h.size = 1.5f; h.particle_radius = 0.01f; h.time_scale = 0.012f; h.steps = 42; h.time = 0.7;
+    h.stiffness = 60.0f; h.gravity_direction[1] = -1.0f; h.has_mouse_ray = 1; h.mouse_dir[2] = 1.0f;
     util::saveCheckpoint(argv[1], h, ps);
     util::CheckpointHeader g;
     std::vector<Particle> back = util::loadCheckpoint(argv[1], &g);
     ok = ok && back.size() == 3 && back[1].position.z == 3 && back[2].pressure == 7.5f && g.steps == 42 &&
-         g.num_particles == 3 && g.size == 1.5f && g.time == 0.7;
+         g.num_particles == 3 && g.size == 1.5f && g.time == 0.7 && g.version == 2 &&
+         g.stiffness == 60.0f && g.gravity_direction[1] == -1.0f && g.has_mouse_ray == 1 &&
+         g.mouse_dir[2] == 1.0f;
     bool threw = false;
     try { util::loadCheckpoint(argv[2], nullptr); } catch (const core::Error&) { threw = true; }
+    if (argc > 3) {  // a version-1 file: 64-byte header, no step parameters
+        util::CheckpointHeader v1;
+        std::vector<Particle> old = util::loadCheckpoint(argv[3], &v1);
+        ok = ok && v1.version == 1 && old.size() == 3 && old[2].pressure == 7.5f && v1.steps == 42;
+    }
     std::printf(ok && threw ? "ok\n" : "FAILED\n");
     return ok && threw ? 0 : 1;
 }
@@ -142,9 +150,23 @@ def test_scene_registry_and_checkpoint_file(exe, tmp_path):
     res = subprocess.run([str(probe), str(ckpt), str(bad)], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     raw = ckpt.read_bytes()
-    assert raw[:6] == b"WCB200" and len(raw) == 64 + 3 * 32
-    got = np.frombuffer(raw, np.float32, offset=64).reshape(-1, 8)
+    assert raw[:6] == b"WCB200" and len(raw) == 160 + 3 * 32        # version-2 header
+    got = np.frombuffer(raw, np.float32, offset=160).reshape(-1, 8)
     assert got[1, 2] == 3.0 and got[2, 7] == 7.5
+    # a header that promises more particles than the file holds is rejected BEFORE any
+    # allocation is sized from it (and a version-1 file, 64-byte header, still loads)
+    lying = bytearray(raw)
+    lying[12:16] = (2_000_000_000).to_bytes(4, "little")
+    (tmp_path / "lying.wcb").write_bytes(bytes(lying))
+    res = subprocess.run([str(probe), str(tmp_path / "c2.wcb"), str(tmp_path / "lying.wcb")],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    v1 = bytearray(raw[:64] + raw[160:])
+    v1[8:12] = (1).to_bytes(4, "little")
+    (tmp_path / "v1.wcb").write_bytes(bytes(v1))
+    res = subprocess.run([str(probe), str(tmp_path / "c3.wcb"), str(bad), str(tmp_path / "v1.wcb")],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
 
 
 @pytest.mark.gpu
@@ -165,3 +187,41 @@ def test_checkpoint_restore_continues_bit_identically(exe, tmp_path):
     # the on-device reduction agrees with the host loop over the downloaded buffer
     assert stats["device"]["invalid"] == stats["invalid"] == 0
     assert stats["device"]["kinetic_energy"] == pytest.approx(stats["kinetic_energy"], rel=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [2, 3])
+def test_headless_decomposed_run_equals_single_device(exe, tmp_path, gpus):
+    """North star: the host code of the decomposed scenes is C++ with the Fluid surface.
+    `wc_headless --gpus N` = core::Fluid::devices(N): N z-slabs driven by ONE process and thread
+    (wc_slab_peer_attach + asynchronous wc_slab_step_peer), buffer 1 read back as the slabs in z
+    order -- bit-identical to the single-device run.  (On a box with fewer devices the slabs
+    share them; the multi-GPU bench covers distinct devices.)"""
+    one, many = tmp_path / "one.bin", tmp_path / "many.bin"
+    args = ["--particles", "60000", "--size", "0.9", "--grid", "18", "--steps", "12"]
+    subprocess.run([exe, *args, "--dump", str(one)], check=True, capture_output=True)
+    res = subprocess.run([exe, *args, "--gpus", str(gpus), "--dump", str(many)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    stats = json.loads(res.stdout.strip().splitlines()[-1])
+    assert stats["particles"] == 60000 and stats["invalid"] == 0
+    assert stats["device"]["kinetic_energy"] == pytest.approx(stats["kinetic_energy"], rel=1e-9)
+    assert np.array_equal(np.fromfile(many, np.float32), np.fromfile(one, np.float32))
+
+
+@pytest.mark.gpu
+def test_checkpoint_carries_the_step_parameters(exe, tmp_path):
+    """Version-2 checkpoints store the per-step parameters: a run with non-default stiffness /
+    viscosity / rest density restores and continues bit-identically WITHOUT the flags repeated
+    (also across the decomposed driver: saved from 2 slabs, restored on one device)."""
+    straight, first, second = tmp_path / "s.bin", tmp_path / "a.wcb", tmp_path / "b.bin"
+    phys = ["--stiffness", "60", "--viscosity", "120", "--rest-density", "650"]
+    subprocess.run([exe, "--particles", "30000", "--steps", "16", *phys, "--dump", str(straight)],
+                   check=True, capture_output=True)
+    subprocess.run([exe, "--particles", "30000", "--steps", "8", *phys, "--gpus", "2",
+                    "--checkpoint", str(first)], check=True, capture_output=True)
+    res = subprocess.run([exe, "--restore", str(first), "--steps", "8", "--dump", str(second)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert json.loads(res.stdout.strip().splitlines()[-1])["total_steps"] == 16
+    assert np.array_equal(np.fromfile(second, np.float32), np.fromfile(straight, np.float32))

@@ -144,6 +144,99 @@ def test_rebalance_mid_run_equals_whole_grid(capi):
         b.close()
 
 
+def _attached_backends(sc, world, d, **kw):
+    hist = np.bincount(slab.layer_of(sc.particles[:, 2], d.bin_size, sc.grid_res),
+                       minlength=sc.grid_res)
+    cuts = slab.slab_cuts(hist, world)
+    parts = slab.decompose(sc.particles, cuts, d.bin_size, sc.grid_res)
+    backends = []
+    for r in range(world):
+        args = dict(capacity=sc.n, ghost_capacity=sc.n, migrant_capacity=8192)
+        args.update(kw)
+        b = slab.CudaSlabBackend(scene_params(sc), cuts[r], cuts[r + 1], **args)
+        b.upload(parts[r])
+        backends.append(b)
+    slab.attach_peers_local(backends)
+    return backends
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_async_steps_one_host_thread_equal_whole_grid(capi, world):
+    """wc_slab_step_peer(info = NULL): whole steps queued handle after handle by ONE host thread,
+    several steps ahead, with no host wait anywhere inside -- what core::Fluid::devices and
+    wc_headless --gpus N do.  The counts of a step exist on the device only; the host reads them
+    when it downloads.  Same bits as the whole-grid run."""
+    sc = make_scene(80000, seed=11)
+    steps = 14   # far more launches than a stream's queue holds: the library bounds the run-ahead
+    ref = whole_grid_run(capi, sc, steps)
+    d = capi.derive(capi.default_params(num_particles=sc.n, **scene_params(sc)))
+    backends = _attached_backends(sc, world, d)
+    slab.run_steps_peer_async(backends, FRAME_DT, steps=3)         # three steps without a look
+    buf1 = np.concatenate([b.download(1) for b in backends])
+    np.testing.assert_array_equal(buf1, ref[2][0])
+    slab.run_steps_peer_async(backends, FRAME_DT, steps=steps - 3)
+    assert sum(b.num_particles for b in backends) == sc.n
+    np.testing.assert_array_equal(np.concatenate([b.download(2) for b in backends]), ref[-1][1])
+    np.testing.assert_array_equal(np.concatenate([b.download(1) for b in backends]), ref[-1][0])
+    for b in backends:
+        b.close()
+
+
+def test_step_peer_host_equals_upload_step_download(capi):
+    """wc_slab_step_peer_host (host AoS in and out per rank, the update kernel storing into the
+    page-locked output itself) equals upload + step + download, chained over several steps."""
+    import torch
+
+    sc = make_scene(60000, seed=13)
+    world, steps = 2, 3
+    ref = whole_grid_run(capi, sc, steps)
+    d = capi.derive(capi.default_params(num_particles=sc.n, **scene_params(sc)))
+    backends = _attached_backends(sc, world, d)
+    cap = sc.n
+    h_in = [torch.empty((cap, 8), dtype=torch.float32, pin_memory=True) for _ in range(world)]
+    h_out = [torch.full((cap, 8), float("nan"), dtype=torch.float32, pin_memory=True)
+             for _ in range(world)]
+    n_cur = []
+    for r, b in enumerate(backends):
+        cur = b.download(1)
+        n_cur.append(cur.shape[0])
+        h_in[r][:n_cur[r]].copy_(torch.from_numpy(cur))
+    for s in range(steps):
+        # one host thread, synchronous calls: queue every rank's step first (async), then the
+        # host round trip of each rank would deadlock on its neighbour -- so ranks run in threads
+        import threading
+
+        infos = [None] * world
+
+        def run(r):
+            infos[r] = backends[r].fluid.slab_step_peer_host((h_in[r].data_ptr(), n_cur[r]),
+                                                            h_out[r].data_ptr(), cap, FRAME_DT)
+
+        ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        got = np.concatenate([h_out[r][:infos[r]["n_owned"]].numpy() for r in range(world)])
+        np.testing.assert_array_equal(got, ref[s][0], err_msg=f"step {s}")
+        n_cur = [infos[r]["n_owned"] for r in range(world)]
+        h_in, h_out = h_out, h_in
+    for b in backends:
+        b.close()
+
+
+def test_overflow_in_an_async_step_is_sticky_and_harmless(capi):
+    """A capacity overflow inside an asynchronous step cannot be reported by that call: the step
+    turns itself off on the device (no index derived from the counts is used), the error word
+    stays set, and the host meets it at its next look."""
+    sc = make_scene(40000, seed=15)
+    d = capi.derive(capi.default_params(num_particles=sc.n, **scene_params(sc)))
+    backends = _attached_backends(sc, 2, d, ghost_capacity=64)    # far too small a halo
+    slab.run_steps_peer_async(backends, FRAME_DT, steps=2)
+    with pytest.raises(capi.WcError):
+        backends[0].fluid.slab_step_peer(FRAME_DT)                 # synchronous: reports
+    for b in backends:
+        b.close()
+
+
 def test_slab_capacity_overflow_is_reported(capi):
     sc = make_scene(20000)
     b = slab.CudaSlabBackend(scene_params(sc), 0, sc.grid_res, capacity=sc.n, ghost_capacity=16,

@@ -27,13 +27,13 @@ PARTICLE_DTYPE = np.dtype(
 # Every symbol include/wc_sph.h declares (checked by tests/test_capi_cpu.py).
 EXPORTS = (
     "wc_abi_version", "wc_last_error", "wc_default_params", "wc_default_step_params", "wc_derive",
-    "wc_create", "wc_destroy", "wc_get_derived", "wc_upload_particles", "wc_download_particles",
-    "wc_step", "wc_step_host", "wc_sort_only", "wc_density_only", "wc_update_only", "wc_download_cells",
+    "wc_device_count", "wc_create", "wc_destroy", "wc_get_derived", "wc_upload_particles", "wc_download_particles",
+    "wc_step", "wc_step_host", "wc_step_export", "wc_sort_only", "wc_density_only", "wc_update_only", "wc_download_cells",
     "wc_download_forces", "wc_upload_sorted", "wc_device_ptrs", "wc_export_aos_device", "wc_sync",
     "wc_stage_times", "wc_launch_count", "wc_slab_get_view", "wc_slab_clear_recv",
     "wc_slab_sort_count", "wc_slab_sync_info", "wc_slab_reorder", "wc_slab_density",
     "wc_slab_update", "wc_advect_only", "wc_slab_ipc_export", "wc_slab_peer_open",
-    "wc_slab_peer_attach", "wc_diagnose", "wc_slab_step_peer",
+    "wc_slab_peer_attach", "wc_diagnose", "wc_slab_step_peer", "wc_slab_step_peer_host",
 )
 
 
@@ -130,6 +130,7 @@ def lib():
             "wc_default_params": [C.POINTER(Params)],
             "wc_default_step_params": [C.POINTER(StepParams)],
             "wc_derive": [C.POINTER(Params), C.POINTER(Derived)],
+            "wc_device_count": [C.POINTER(C.c_int32)],
             "wc_create": [C.POINTER(Params), C.POINTER(vp)],
             "wc_destroy": [vp],
             "wc_get_derived": [vp, C.POINTER(Derived)],
@@ -137,6 +138,7 @@ def lib():
             "wc_download_particles": [vp, i32, vp],
             "wc_step": [vp, f32, C.POINTER(StepParams)],
             "wc_step_host": [vp, f32, C.POINTER(StepParams), vp, C.c_int32, vp],
+            "wc_step_export": [vp, f32, C.POINTER(StepParams), vp],
             "wc_sort_only": [vp],
             "wc_density_only": [vp, C.POINTER(StepParams)],
             "wc_update_only": [vp, f32, C.POINTER(StepParams)],
@@ -161,6 +163,8 @@ def lib():
             "wc_slab_peer_attach": [vp, i32, vp],
             "wc_diagnose": [vp, i32, f32, C.POINTER(Diagnostics)],
             "wc_slab_step_peer": [vp, f32, C.POINTER(StepParams), C.POINTER(C.c_int32 * 8)],
+            "wc_slab_step_peer_host": [vp, f32, C.POINTER(StepParams), vp, i32, vp, i32,
+                                       C.POINTER(C.c_int32 * 8)],
         }
         for name, argtypes in sig.items():
             fn = getattr(L, name)
@@ -297,6 +301,16 @@ class Fluid:
         check(lib().wc_step_host(self._h, float(frame_dt), C.byref(self.step_params),
                                  C.c_void_p(ptr), int(n), C.c_void_p(host_out)))
 
+    def step_export(self, aos_dst, frame_dt=1.0 / 60.0):
+        """Fluid::update with the new buffer 1 also stored as 32-byte AoS records into the
+        device-addressable buffer at raw pointer `aos_dst` (wc_step_export)."""
+        check(lib().wc_step_export(self._h, float(frame_dt), C.byref(self.step_params),
+                                   C.c_void_p(aos_dst)))
+
+    def export_aos_device(self, which, device_ptr):
+        """Pack buffer `which` (1 or 2) as 32-byte AoS into device memory (wc_export_aos_device)."""
+        check(lib().wc_export_aos_device(self._h, int(which), C.c_void_p(device_ptr)))
+
     def sort_only(self):
         check(lib().wc_sort_only(self._h))
 
@@ -350,11 +364,24 @@ class Fluid:
     def slab_update(self, frame_dt=1.0 / 60.0):
         check(lib().wc_slab_update(self._h, float(frame_dt), C.byref(self.step_params)))
 
-    def slab_step_peer(self, frame_dt=1.0 / 60.0) -> dict:
-        """The five slab phases as one call (all neighbours attached); returns the step's info."""
+    def slab_step_peer(self, frame_dt=1.0 / 60.0, wait=True):
+        """The five slab phases as one call (all neighbours attached).  wait=True: returns the
+        step's info; wait=False: only queues the step (no host wait anywhere in it)."""
+        if not wait:
+            check(lib().wc_slab_step_peer(self._h, float(frame_dt), C.byref(self.step_params), None))
+            return None
         info = (C.c_int32 * 8)()
         check(lib().wc_slab_step_peer(self._h, float(frame_dt), C.byref(self.step_params),
                                       C.byref(info)))
+        return dict(zip(SLAB_INFO, [int(x) for x in info]))
+
+    def slab_step_peer_host(self, host_in, host_out, out_capacity, frame_dt=1.0 / 60.0) -> dict:
+        """wc_slab_step_peer_host: host AoS in (pointer, n) or None, host AoS out (raw pointer)."""
+        ptr, n = host_in if host_in is not None else (None, 0)
+        info = (C.c_int32 * 8)()
+        check(lib().wc_slab_step_peer_host(self._h, float(frame_dt), C.byref(self.step_params),
+                                           C.c_void_p(ptr), int(n), C.c_void_p(host_out),
+                                           int(out_capacity), C.byref(info)))
         return dict(zip(SLAB_INFO, [int(x) for x in info]))
 
     # -- peer-memory exchange (include/wc_sph.h, wc_slab_peer_*)

@@ -135,19 +135,24 @@ struct wc_handle {
     int zbase = 0;               // global layer of local layer 0
     int M = 0;                   // migrant slots on either side of buffer 1's owned region
     int Cg = 0;                  // ghost slots on either side of buffer 2's owned region
-    int n_first = 0, n_last = 0, n_glow = 0, n_ghigh = 0;  // of the current step (host copies)
-    int n_in_old = 0;            // owned count of the input (before this step's migration)
-    bool info_valid = false;
+    int n_first = 0, n_last = 0, n_glow = 0, n_ghigh = 0;  // of the last step the host looked at
+    int m_in_host[2] = {0, 0};
+    // The step's own counts live on the device (wc::SlabDyn); the host copies above and `n` are
+    // refreshed only when somebody asks (slab_sync_host), so a step never waits for the host.
+    wc::SlabDyn* dyn = nullptr;
+    bool host_stale = false;     // steps were queued since the host copies were refreshed
+    // Asynchronous steps run at most kRunAhead steps ahead of the device: the launch queue of a
+    // stream is finite, and a host thread that blocks in a launch on one handle can no longer
+    // queue the work a neighbouring handle of the same thread is waiting for.
+    static constexpr int kRunAhead = 4;
+    cudaEvent_t step_done[kRunAhead] = {};
+    uint32_t ghost_step = 0;     // step_no whose ghost tables have been queued
+    uint32_t* done = nullptr;    // [8] last-block counters of the signalling kernels (in arena)
     float4* mig_out[2] = {nullptr, nullptr};   // [0] to rank-1, [1] to rank+1 (header + AoS)
     float4* mig_in[2] = {nullptr, nullptr};    // [0] from rank-1, [1] from rank+1
     uint32_t* lc_send[2] = {nullptr, nullptr}; // layer-count messages [n, G*G counts]
     uint32_t* lc_recv[2] = {nullptr, nullptr};
-    uint32_t* flags = nullptr;                 // migrant flags / slots scratch (2 x cap each)
-    uint32_t* slots = nullptr;
-    uint32_t* errors = nullptr;                // sticky device-side error counter
-    uint32_t* m_in = nullptr;                  // [2] received migrant counts (in arena)
-    uint32_t* info_dev = nullptr;              // [8] (in arena)
-    uint32_t* info_host = nullptr;             // pinned
+    uint32_t* info_host = nullptr;             // pinned: this step's counts (k_ghost_tables)
     unsigned long long* scan_status_x[4] = {}; // extra scan states: ghost-low, ghost-high, mig 0/1
     unsigned int* scan_counter_x[4] = {};
     size_t mig_bytes = 0, lc_bytes = 0;
@@ -167,6 +172,11 @@ struct wc_handle {
     uint32_t* sig = nullptr;        // [kSigPhases * 2]: raised by the neighbours
     uint32_t step_no = 0;
     bool peer_mode() const { return peer[0].on || peer[1].on; }
+    // A neighbour on the SAME device (virtual ranks of the tests): a kernel whose every block
+    // spins for that neighbour's signal could keep the neighbour's own kernels off the SMs, so
+    // the waits then stay stand-alone one-block kernels in front of the consumers.
+    bool same_device_peer = false;
+    bool fused_waits() const { return peer_mode() && !same_device_peer; }
 };
 
 enum { kSigLc = 0, kSigHaloPos = 1, kSigHaloRho = 2, kSigMig = 3, kSigPhases = 4 };
@@ -210,68 +220,97 @@ int record(wc_handle* h, int idx) {
     return WC_OK;
 }
 
-// ---- peer-memory exchange helpers (no-ops unless wc_slab_peer_* attached a neighbour)
-// Blocks this handle's stream until both attached neighbours have raised `phase` to `value`.
-int peer_wait(wc_handle* h, int phase, uint32_t value) {
-    if (!h->peer_mode() || value == 0) return WC_OK;
-    const uint32_t* fa = h->peer[0].on ? h->sig + phase * 2 + 0 : nullptr;
-    const uint32_t* fb = h->peer[1].on ? h->sig + phase * 2 + 1 : nullptr;
-    k_wait_signals<<<1, 2, 0, h->stream>>>(fa, fb, value);
-    WC_CHECK_LAUNCH(h);
+enum { kDoneInfo = 0, kDoneGhost = 1, kDoneSort = 2, kDoneDensity = 3, kDoneMigrants = 4,
+       kDoneStandAlone = -2 };
+
+// What a slab kernel gets beyond its arrays (wc_common.cuh SlabRef): the device record, the
+// attached neighbours' buffer 2, and -- peer mode only -- the local flags it waits on
+// (wait_phase, -1: none) and the neighbours' flags its last block raises (raise_phase, with
+// its block counter `done_slot`).  `value` is the step number waited for / raised.
+SlabRef slab_ref(const wc_handle* h, int wait_phase = -1, int raise_phase = -1, int done_slot = -1,
+                 long long value = -1) {
+    SlabRef r = SlabRef();
+    if (!h->slab) return r;
+    r.dyn = h->dyn;
+    r.Cg = (uint32_t)h->Cg;
+    r.cap = (uint32_t)h->cap;
+    r.step_no = value >= 0 ? (uint32_t)value : h->step_no;
+    if (done_slot >= 0) r.done = h->done + done_slot;
+    for (int d = 0; d < 2; d++) {
+        if (!h->peer[d].on) continue;
+        r.peer_pos[d] = h->peer[d].pos1;
+        r.peer_vel[d] = h->peer[d].vel1;
+        if (wait_phase >= 0 && (h->fused_waits() || done_slot == kDoneStandAlone))
+            r.wait[d] = h->sig + wait_phase * 2 + d;
+        // the neighbour in direction d sees this rank as its direction 1 - d
+        if (raise_phase >= 0) r.raise[d] = h->peer[d].sig + raise_phase * 2 + (1 - d);
+    }
+    return r;
+}
+
+// The host copies of the step's counts, on demand: waits for the stream, then reads the
+// page-locked record k_ghost_tables stored and the sticky error word.
+int slab_sync_host(wc_handle* h, bool report = true) {
+    if (!h->slab || !h->host_stale) return WC_OK;
+    uint32_t err = 0;
+    WC_CUDA(cudaMemcpyAsync(&err, &h->dyn->errors, sizeof(err), cudaMemcpyDeviceToHost, h->stream));
+    WC_CUDA(cudaStreamSynchronize(h->stream));
+    const uint32_t* hi = h->info_host;
+    h->n = (int)hi[0];
+    h->n_first = (int)hi[1], h->n_last = (int)hi[2];
+    h->n_glow = (int)hi[3], h->n_ghigh = (int)hi[4];
+    h->m_in_host[0] = (int)hi[6], h->m_in_host[1] = (int)hi[7];
+    h->peer[0].n_owned = (int)hi[8], h->peer[1].n_owned = (int)hi[9];
+    h->info_host[5] = err;
+    h->host_stale = false;
+    if (h->n > h->cap) h->n = h->cap;  // the step is dead (kSlabErrOwned); keep host copies in range
+    // an asynchronous step cannot report: its sticky error word is met here, at the next look
+    if (err && report)
+        return fail(err & kSlabErrTimeout ? WC_ERR_CUDA : WC_ERR_CAPACITY,
+                    "a queued slab step failed (error bits 0x%x:%s%s%s%s%s%s); counts of the failing "
+                    "step: %u owned (capacity %d), boundary layers %u / %u, ghosts %u / %u (ghost "
+                    "capacity %d), migrant capacity %d", err,
+                    err & kSlabErrOwned ? " owned-capacity" : "", err & kSlabErrGhost ? " ghost-capacity" : "",
+                    err & kSlabErrHalo ? " halo-layer>neighbour-ghost-capacity" : "",
+                    err & kSlabErrMigrants ? " migrant-capacity" : "",
+                    err & kSlabErrStray ? " stray-migrant(moved>1-layer)" : "",
+                    err & kSlabErrTimeout ? " neighbour-signal-timeout" : "", hi[0], h->cap, hi[1],
+                    hi[2], hi[3], hi[4], h->Cg, h->M);
     return WC_OK;
 }
 
-// Raises `phase` at the neighbour in direction d (it sees the signal as coming from 1 - d).
-int peer_signal(wc_handle* h, int d, int phase) {
-    k_signal<<<1, 1, 0, h->stream>>>(h->peer[d].sig + phase * 2 + (1 - d), h->step_no);
-    WC_CHECK_LAUNCH(h);
-    return WC_OK;
-}
-
-// Where this rank's halo layers live in the attached neighbours (see PeerHalo).  The layer sent
-// down becomes the lower neighbour's ghost-high slice (right after its owned particles), the
-// layer sent up the upper neighbour's ghost-low slice (right before them).  Needs the counts
-// of wc_slab_sync_info.
-PeerHalo peer_halo(const wc_handle* h) {
-    PeerHalo ph = PeerHalo();
-    if (!h->peer_mode()) return ph;
-    ph.n_first = (uint32_t)h->n_first;
-    ph.hi_begin = (uint32_t)(h->n - h->n_last);
-    if (h->peer[0].on) {
-        ph.pos[0] = h->peer[0].pos1, ph.vel[0] = h->peer[0].vel1;
-        ph.dst[0] = (uint32_t)(h->Cg + h->peer[0].n_owned);
-    }
-    if (h->peer[1].on) {
-        ph.pos[1] = h->peer[1].pos1, ph.vel[1] = h->peer[1].vel1;
-        ph.dst[1] = (uint32_t)(h->Cg - h->n_last);
-    }
-    return ph;
-}
-
-// The same halo as explicit peer copies: only for the simple cross-check kernels
-// (WC_FLAG_SIMPLE_KERNELS), whose density pass has no remote stores.
+// Host view of where this rank's halo layers live in the attached neighbours: only for the
+// simple cross-check kernels (WC_FLAG_SIMPLE_KERNELS), whose density pass has no remote
+// stores, so the halo goes as explicit peer copies.  Needs slab_sync_host.
 int peer_copy_halo(wc_handle* h) {
-    const PeerHalo ph = peer_halo(h);
     for (int d = 0; d < 2; d++) {
         if (!h->peer[d].on) continue;
         const size_t n_layer = (size_t)(d == 0 ? h->n_first : h->n_last);
-        const size_t src = (size_t)h->Cg + (d == 0 ? 0 : (size_t)ph.hi_begin);
+        const size_t src = (size_t)h->Cg + (d == 0 ? 0 : (size_t)(h->n - h->n_last));
+        const size_t dst = d == 0 ? (size_t)h->Cg + h->peer[0].n_owned : (size_t)h->Cg - h->n_last;
         if (n_layer == 0) continue;
-        WC_CUDA(cudaMemcpyAsync(ph.pos[d] + ph.dst[d], h->pos[1] + src, n_layer * sizeof(float4),
+        WC_CUDA(cudaMemcpyAsync(h->peer[d].pos1 + dst, h->pos[1] + src, n_layer * sizeof(float4),
                                 cudaMemcpyDeviceToDevice, h->stream));
-        WC_CUDA(cudaMemcpyAsync(ph.vel[d] + ph.dst[d], h->vel[1] + src, n_layer * sizeof(float4),
+        WC_CUDA(cudaMemcpyAsync(h->peer[d].vel1 + dst, h->vel[1] + src, n_layer * sizeof(float4),
                                 cudaMemcpyDeviceToDevice, h->stream));
     }
     return WC_OK;
 }
 
-// Tells both attached neighbours that this step's `phase` data is in their buffers (the
-// producing kernel stored it there itself).
-int peer_signal_both(wc_handle* h, int phase) {
-    int rc;
-    for (int d = 0; d < 2; d++)
-        if (h->peer[d].on && (rc = peer_signal(h, d, phase))) return rc;
+// Stand-alone wait and / or signal, a one-block kernel: for the simple cross-check kernels,
+// which carry neither, and for the waits of handles whose neighbour shares the device.
+int slab_sync_kernel(wc_handle* h, int wait_phase, int raise_phase, int done_slot, long long value = -1) {
+    if (!h->slab || !h->peer_mode()) return WC_OK;
+    SlabRef r = slab_ref(h, wait_phase, raise_phase, done_slot >= 0 ? done_slot : kDoneStandAlone, value);
+    k_slab_sync<<<1, 32, 0, h->stream>>>(r);
+    WC_CHECK_LAUNCH(h);
     return WC_OK;
+}
+
+// The wait in front of a consumer kernel when it cannot ride inside the kernel.
+int slab_pre_wait(wc_handle* h, int phase, long long value = -1) {
+    if (!h->slab || !h->peer_mode() || h->fused_waits()) return WC_OK;
+    return slab_sync_kernel(h, phase, -1, -1, value);
 }
 
 // Sort::run part 1 (Sort.cpp:255-259): clear, count, scan.  In slab mode the input is the
@@ -298,19 +337,17 @@ int sort_count_phase(wc_handle* h, bool timed) {
         if (timed && (rc = record(h, 2))) return rc;
         return WC_OK;
     }
-    const int G2 = G * G, M = h->M, n_old = h->n_in_old, total = M + n_old + M;
+    const int G2 = G * G, M = h->M;
     h->step_no++;
-    if ((rc = peer_wait(h, kSigMig, h->step_no - 1))) return rc;  // last step's migrants
-    // received migrants -> the slots before / after the owned region of buffer 1
-    k_unpack_migrants<<<div_up(M, 256), 256, 0, h->stream>>>(h->mig_in[0], M, h->pos[0], h->vel[0],
-                                                           h->m_in + 0);
+    h->host_stale = true;
+    // (waits for, and) unpacks last step's migrants -> the slots before / after the owned region
+    if ((rc = slab_pre_wait(h, kSigMig, (long long)h->step_no - 1))) return rc;
+    k_slab_begin<<<div_up(2 * M, 256), 256, 0, h->stream>>>(
+        h->mig_in[0], h->mig_in[1], M, h->pos[0], h->vel[0],
+        slab_ref(h, kSigMig, -1, -1, (long long)h->step_no - 1));
     WC_CHECK_LAUNCH(h);
-    k_unpack_migrants<<<div_up(M, 256), 256, 0, h->stream>>>(
-        h->mig_in[1], M, h->pos[0] + M + n_old, h->vel[0] + M + n_old, h->m_in + 1);
-    WC_CHECK_LAUNCH(h);
-    k_hash_count_slab<<<div_up(total, 256), 256, 0, h->stream>>>(
-        h->pos[0], total, M, n_old, h->m_in, bin, G, h->z_begin, h->z_end, h->cell_ids, h->ranks,
-        h->counts, h->errors);
+    k_hash_count_slab<<<div_up(M + h->cap + M, 256), 256, 0, h->stream>>>(
+        h->pos[0], M, h->dyn, bin, G, h->z_begin, h->z_end, h->cell_ids, h->ranks, h->counts);
     WC_CHECK_LAUNCH(h);
     if (timed && (rc = record(h, 1))) return rc;
     const int owned_bins = (h->Lz - 2) * G2;
@@ -318,47 +355,60 @@ int sort_count_phase(wc_handle* h, bool timed) {
         h->counts + G2, h->offsets + G2, owned_bins, h->scan_status, h->scan_counter,
         (uint32_t)h->Cg);
     WC_CHECK_LAUNCH(h);
-    k_slab_info<<<div_up(G2, 256), 256, 0, h->stream>>>(h->counts, h->offsets, G2, h->Lz,
-                                                       (uint32_t)h->Cg, h->info_dev,
-                                                       h->lc_send[0], h->lc_send[1],
-                                                       h->peer[0].on ? h->peer[0].lc_recv : nullptr,
-                                                       h->peer[1].on ? h->peer[1].lc_recv : nullptr);
-    WC_CHECK_LAUNCH(h);  // peer mode: the kernel stored the layer counts in the neighbours itself
-    if ((rc = peer_signal_both(h, kSigLc))) return rc;
+    // counts into the slab record; layer counts to the neighbours (stored there directly in
+    // peer mode, whose last block raises the flags)
+    k_slab_info<<<div_up(G2, 256), 256, 0, h->stream>>>(
+        h->counts, h->offsets, G2, h->Lz, h->lc_send[0], h->lc_send[1],
+        h->peer[0].on ? h->peer[0].lc_recv : nullptr, h->peer[1].on ? h->peer[1].lc_recv : nullptr,
+        slab_ref(h, -1, kSigLc, kDoneInfo));
+    WC_CHECK_LAUNCH(h);
     if (timed && (rc = record(h, 2))) return rc;
-    h->info_valid = false;
     return WC_OK;
 }
 
-// Sort::run part 2 (Sort.cpp:263-264): the stable reorder into buffer 2.
+// The ghost layers of the table from the neighbours' layer-count messages (queued once per step).
+int slab_ghost_phase(wc_handle* h) {
+    if (h->ghost_step == h->step_no) return WC_OK;
+    const int G2 = h->p.grid_res * h->p.grid_res;
+    int rcw = slab_pre_wait(h, kSigLc);
+    if (rcw) return rcw;
+    k_ghost_tables<<<2, kScanThreads, 0, h->stream>>>(h->lc_recv[0], h->lc_recv[1], G2, h->Lz,
+                                                     h->counts, h->offsets, h->info_host,
+                                                     slab_ref(h, kSigLc, -1, kDoneGhost));
+    WC_CHECK_LAUNCH(h);
+    h->ghost_step = h->step_no;
+    return WC_OK;
+}
+
+// Sort::run part 2 (Sort.cpp:263-264): the stable reorder into buffer 2.  n_in / n_sorted:
+// sizes of the input and of the sorted array -- in slab mode launch bounds only (the kernels
+// read the true counts from the slab record).
 int sort_reorder_phase(wc_handle* h, bool timed, int n_in, int n_sorted) {
     const int G = h->p.grid_res;
     const float bin = h->d.bin_size;
     int rc;
-    if (n_in > 0 && n_sorted > 0) {
-        k_scatter_ids<<<div_up(n_in, 256), 256, 0, h->stream>>>(h->cell_ids, h->ranks, h->offsets,
-                                                                 n_in, h->ids, (uint32_t)h->Cg);
+    const bool moved = n_in > 0 && n_sorted > 0;
+    const ReorderIO io{h->pos[0], h->vel[0], h->pos[1] + h->Cg, h->vel[1] + h->Cg, h->perm};
+    if (moved) {
+        k_scatter_ids<<<div_up(n_in, 256), 256, 0, h->stream>>>(
+            h->cell_ids, h->ranks, h->offsets, n_in, h->ids, (uint32_t)h->Cg, slab_ref(h), h->M);
         WC_CHECK_LAUNCH(h);
-        const ReorderIO io{h->pos[0], h->vel[0], h->pos[1] + h->Cg, h->vel[1] + h->Cg, h->perm,
-                           h->slab ? peer_halo(h) : PeerHalo()};
         k_reorder<<<div_up(n_sorted, 256), 256, 0, h->stream>>>(
-            h->ids, h->offsets, n_sorted, bin, G, h->zbase, (uint32_t)h->Cg, io, h->big_cells,
-            h->big_count, (uint32_t)h->big_cap);
+            h->ids, h->offsets, n_sorted, bin, G, h->zbase, (uint32_t)h->Cg, io, slab_ref(h),
+            h->big_cells, h->big_count, (uint32_t)h->big_cap);
         WC_CHECK_LAUNCH(h);
     }
-    {   // group table for the gathers + the cells above kBigCell particles, one launch
+    {   // group table for the gathers + the cells above kBigCell particles, one launch; in peer
+        // mode its last block tells the neighbours that the halo positions are in their ghost slots
         const int row0 = h->slab ? G : 0, row1 = h->slab ? (h->Lz - 1) * G : h->Lz * G;
-        const bool moved = n_in > 0 && n_sorted > 0;
-        const ReorderIO io{h->pos[0], h->vel[0], h->pos[1] + h->Cg, h->vel[1] + h->Cg, h->perm,
-                           h->slab ? peer_halo(h) : PeerHalo()};
         int bits = 1;  // IDs index the (virtual) input: that many radix passes
         while (bits < 32 && (1ll << bits) < (long long)n_in) bits++;
-        if (h->groups || moved) {
+        if (h->groups || moved || h->slab) {
             k_finish_sort<<<finish_sort_blocks(h->groups ? row1 - row0 : 0), kBigThreads, 0,
                             h->stream>>>(h->offsets, G, row0, row1, h->groups, h->num_groups,
                                          moved ? h->ids : nullptr, h->ranks, (uint32_t)h->Cg, io,
-                                         h->big_cells, h->big_count, (uint32_t)h->big_cap,
-                                         (bits + 7) / 8);
+                                         slab_ref(h, -1, kSigHaloPos, kDoneSort), h->big_cells,
+                                         h->big_count, (uint32_t)h->big_cap, (bits + 7) / 8);
             WC_CHECK_LAUNCH(h);
         }
     }
@@ -369,8 +419,9 @@ int sort_reorder_phase(wc_handle* h, bool timed, int n_in, int n_sorted) {
 }
 
 GroupTable group_table(const wc_handle* h) {
+    // launch bound: from the particle count the host knows -- in slab mode the capacity
     return GroupTable{h->groups, h->num_groups,
-                      max_groups(h->n, (long long)h->Lz * h->p.grid_res)};
+                      max_groups(h->slab ? h->cap : h->n, (long long)h->Lz * h->p.grid_res)};
 }
 
 int run_sort(wc_handle* h, bool timed) {
@@ -380,7 +431,7 @@ int run_sort(wc_handle* h, bool timed) {
 }
 
 int run_density(wc_handle* h, const wc_step_params& sp) {
-    if (h->n == 0) return WC_OK;
+    if (!h->slab && h->n == 0) return WC_OK;
     const SphConsts c = make_consts(h, sp, 0.0f);
     const bool dbg = h->p.flags & WC_FLAG_DEBUG_OUTPUTS;
     const NbrList list{h->nbr_idx, h->nbr_mask, h->nbr_words, h->nbr_cap_words};
@@ -388,7 +439,7 @@ int run_density(wc_handle* h, const wc_step_params& sp) {
     if (!simple)
         launch_density_tile(h->pos[1], h->vel[1], h->offsets, c, group_table(h),
                             dbg ? h->neighbour_counts : nullptr, list, h->stream,
-                            h->slab ? peer_halo(h) : PeerHalo());
+                            slab_ref(h, kSigHaloPos, kSigHaloRho, kDoneDensity));
     h->nbr_valid = !simple && h->nbr_idx != nullptr;
     if (simple) {
         if (dbg)
@@ -404,7 +455,7 @@ int run_density(wc_handle* h, const wc_step_params& sp) {
 
 int run_update(wc_handle* h, const wc_step_params& sp, float frame_dt,
                float4* aos_out = nullptr) {
-    if (h->n == 0) return WC_OK;
+    if (!h->slab && h->n == 0) return WC_OK;
     const SphConsts c = make_consts(h, sp, frame_dt);
     const bool dbg = h->p.flags & WC_FLAG_DEBUG_OUTPUTS;
     // The list is only trusted when the density pass that built it saw these positions.
@@ -414,7 +465,8 @@ int run_update(wc_handle* h, const wc_step_params& sp, float frame_dt,
     const bool simple = h->p.flags & WC_FLAG_SIMPLE_KERNELS;
     if (!simple)
         launch_update_tile(h->pos[1], h->vel[1], h->offsets, c, group_table(h), h->pos[0] + h->M,
-                           h->vel[0] + h->M, dbg ? h->forces : nullptr, list, h->stream, aos_out);
+                           h->vel[0] + h->M, dbg ? h->forces : nullptr, list, h->stream, aos_out,
+                           slab_ref(h, kSigHaloRho));
     if (simple) {
         if (dbg)
             k_update_v1<true><<<div_up(h->n, 128), 128, 0, h->stream>>>(
@@ -430,6 +482,103 @@ int run_update(wc_handle* h, const wc_step_params& sp, float frame_dt,
 
 int check_step_params(const wc_step_params* sp) {
     if (!sp) return fail(WC_ERR_INVALID, "step params are NULL");
+    return WC_OK;
+}
+
+// wc_slab_update: force + integrate (optionally also stored as AoS records into aos_out, a
+// device-addressable buffer), then the extraction of the particles that left the slab.
+int slab_update_impl(wc_handle* h, float frame_dt, const wc_step_params* sp, float4* aos_out) {
+    if (!h) return fail(WC_ERR_INVALID, "handle is NULL");
+    if (!h->slab) return fail(WC_ERR_INVALID, "not a slab handle");
+    WC_CUDA(cudaSetDevice(h->p.device));
+    int rc = check_step_params(sp);
+    if (rc) return rc;
+    if (!h->sorted_valid) return fail(WC_ERR_INVALID, "wc_slab_update needs wc_slab_reorder");
+    const float bin = h->d.bin_size;
+    if (!(50.0f * fabsf(frame_dt * h->p.time_scale) < bin))
+        return fail(WC_ERR_INVALID, "dt too large for one-layer migration: 50 * dt >= binSize");
+    const bool simple = h->p.flags & WC_FLAG_SIMPLE_KERNELS;
+    if (simple) {
+        if ((rc = slab_sync_host(h))) return rc;
+        if ((rc = slab_sync_kernel(h, kSigHaloRho, -1, -1))) return rc;
+    } else if ((rc = slab_pre_wait(h, kSigHaloRho))) {
+        return rc;
+    }
+    if ((rc = run_update(h, *sp, frame_dt, aos_out))) return rc;
+    // Particles whose new z-layer left the slab: only the first / last owned layer can lose
+    // any (|v| dt < binSize), and those layers are the head / tail of the sorted order.
+    const int tiles = div_up(h->Cg, kScanTile) > 0 ? div_up(h->Cg, kScanTile) : 1;
+    k_migrants<<<dim3(tiles, 2), kScanThreads, 0, h->stream>>>(
+        h->pos[0] + h->M, h->vel[0] + h->M, bin, h->p.grid_res, h->z_begin, h->z_end, h->M,
+        h->mig_out[0], h->mig_out[1], h->peer[0].on ? h->peer[0].mig_in : nullptr,
+        h->peer[1].on ? h->peer[1].mig_in : nullptr, h->scan_status_x[2], h->scan_status_x[3],
+        h->scan_counter_x[2], h->scan_counter_x[3], slab_ref(h, -1, kSigMig, kDoneMigrants));
+    WC_CHECK_LAUNCH(h);
+    h->host_stale = true;  // (the next step's input count changed on the device)
+    if ((rc = record(h, 5))) return rc;
+    h->have_times = (h->p.flags & WC_FLAG_STAGE_TIMING) != 0;
+    return WC_OK;
+}
+
+// CUDA loads a kernel lazily, at its first launch, and that load can wait for running kernels.
+// A slab step must never meet it: with the neighbour's work queued by the same host thread, a
+// kernel spinning for that neighbour's signal would block the load that the rest of the queueing
+// is waiting behind.  So a slab handle touches every kernel of the step once, at creation.
+int preload_slab_kernels() {
+    cudaFuncAttributes a;
+    WC_CUDA(cudaFuncGetAttributes(&a, k_slab_begin));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_hash_count_slab));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_scan));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_slab_info));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_ghost_tables));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_scatter_ids));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_reorder));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_finish_sort));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_density_tile<false>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_density_tile<true>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_update_tile<false>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_update_tile<true>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_density_v1<false>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_density_v1<true>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_update_v1<false>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_update_v1<true>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_migrants));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_slab_sync));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_aos_to_soa));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_soa_to_aos));
+    return WC_OK;
+}
+
+// One whole step of a slab handle whose neighbours are attached (or absent): the five phases
+// queued back to back.  info == NULL: returns without waiting for the GPU (nothing in the step
+// depends on a host read-back).  info != NULL: waits and reports the step's counts.
+int slab_step_impl(wc_handle* h, float frame_dt, const wc_step_params* sp, int32_t info[8],
+                   float4* aos_out) {
+    int rc;
+    if (h && h->slab && !info) {  // bound the run-ahead: wait for the step kRunAhead steps back
+        cudaEvent_t ev = h->step_done[(h->step_no + 1) % wc_handle::kRunAhead];
+        if (ev) WC_CUDA(cudaEventSynchronize(ev));
+    }
+    if ((rc = wc_slab_sort_count(h))) return rc;
+    if (h->p.flags & WC_FLAG_SIMPLE_KERNELS) {  // host-sized cross-check kernels: needs the counts
+        int32_t tmp[8];
+        if ((rc = wc_slab_sync_info(h, tmp))) return rc;
+    }
+    if ((rc = wc_slab_reorder(h))) return rc;
+    if ((rc = wc_slab_density(h, sp))) return rc;
+    if ((rc = slab_update_impl(h, frame_dt, sp, aos_out))) return rc;
+    if (!info) {
+        cudaEvent_t& ev = h->step_done[h->step_no % wc_handle::kRunAhead];
+        if (!ev) WC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        WC_CUDA(cudaEventRecord(ev, h->stream));
+        return WC_OK;
+    }
+    h->host_stale = true;
+    if ((rc = slab_sync_host(h, false))) return rc;
+    for (int k = 0; k < 8; k++) info[k] = (int32_t)h->info_host[k];
+    if (info[5] != 0)
+        return fail(WC_ERR_CAPACITY, "slab capacity overflow, lost migrants or a missing neighbour "
+                                     "signal (error bits 0x%x)", (unsigned)info[5]);
     return WC_OK;
 }
 
@@ -490,6 +639,17 @@ int wc_derive(const wc_params* p, wc_derived* d) {
     d->spiky_const = (float)(-45.0 / (pi * std::pow(h, 6)));
     d->visc_const = (float)(45.0 / (pi * std::pow(h, 6)));
     d->dist2_threshold = dist2_threshold(d->kernel_radius);
+    return WC_OK;
+}
+
+int wc_device_count(int32_t* count) {
+    if (!count) return fail(WC_ERR_INVALID, "NULL argument");
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    *count = e == cudaSuccess ? n : 0;
+    if (e != cudaSuccess || n == 0)
+        return fail(WC_ERR_NO_DEVICE, "no CUDA device: %s",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     return WC_OK;
 }
 
@@ -636,8 +796,7 @@ int wc_create(const wc_params* p, wc_handle** out) {
             h->scan_counter_x[k] = (unsigned int*)((char*)h->arena + off + xbytes[k] - 256);
             off += xbytes[k];
         }
-        h->m_in = (uint32_t*)((char*)h->arena + off);
-        h->info_dev = h->m_in + 8;
+        h->done = (uint32_t*)((char*)h->arena + off);  // 8 block counters, zero at every sort
         h->mig_bytes = (size_t)(kMigHeaderFloat4 + 2 * (size_t)h->M) * sizeof(float4);
         h->lc_bytes = (kLcHeader + G2) * sizeof(uint32_t);
         for (int k = 0; k < 2; k++) {
@@ -650,16 +809,19 @@ int wc_create(const wc_params* p, wc_handle** out) {
             cudaMemsetAsync(h->lc_send[k], 0, h->lc_bytes, h->stream);
             cudaMemsetAsync(h->lc_recv[k], 0, h->lc_bytes, h->stream);
         }
-        WC_ALLOC(h->flags, 2 * capz * sizeof(uint32_t));
-        WC_ALLOC(h->slots, 2 * (capz + 1) * sizeof(uint32_t));
-        WC_ALLOC(h->errors, 256);
-        cudaMemsetAsync(h->errors, 0, 256, h->stream);
+        WC_ALLOC(h->dyn, 256);
+        cudaMemsetAsync(h->dyn, 0, 256, h->stream);
         WC_ALLOC(h->sig, 256);
         cudaMemsetAsync(h->sig, 0, 256, h->stream);
         e = cudaMallocHost((void**)&h->info_host, 64);
         if (e != cudaSuccess) {
             wc_destroy(h);
             return fail(WC_ERR_CUDA, "cudaMallocHost: %s", cudaGetErrorString(e));
+        }
+        std::memset(h->info_host, 0, 64);
+        if ((rc = preload_slab_kernels())) {
+            wc_destroy(h);
+            return rc;
         }
     }
 
@@ -718,15 +880,15 @@ int wc_destroy(wc_handle* h) {
         cudaFree(h->lc_send[k]);
         cudaFree(h->lc_recv[k]);
     }
-    cudaFree(h->flags);
-    cudaFree(h->slots);
-    cudaFree(h->errors);
+    cudaFree(h->dyn);
     cudaFree(h->sig);
     for (int d = 0; d < 2; d++)
         if (h->peer[d].ipc)
             for (void* base : h->peer[d].ipc_base)
                 if (base) cudaIpcCloseMemHandle(base);
     if (h->info_host) cudaFreeHost(h->info_host);
+    for (cudaEvent_t ev : h->step_done)
+        if (ev) cudaEventDestroy(ev);
     for (int i = 0; i <= WC_NUM_STAGES; i++)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -746,7 +908,17 @@ static int upload_into(wc_handle* h, int buf, const wc_particle* host_aos, int32
     if (n > h->cap) return fail(WC_ERR_CAPACITY, "n = %d exceeds capacity %d", n, h->cap);
     WC_CUDA(cudaSetDevice(h->p.device));
     h->n = n;
-    if (buf == 0) h->n_in_old = n;
+    if (h->slab) {  // the device record follows: buffer 1's owned count is the next step's input
+        const int rcs = slab_sync_host(h);
+        if (rcs) return rcs;
+        h->n = n;
+        const uint32_t un = (uint32_t)n;
+        if (buf == 0)
+            WC_CUDA(cudaMemcpyAsync(&h->dyn->n_in_old, &un, 4, cudaMemcpyHostToDevice, h->stream));
+        else
+            WC_CUDA(cudaMemcpyAsync(&h->dyn->n, &un, 4, cudaMemcpyHostToDevice, h->stream));
+        WC_CUDA(cudaStreamSynchronize(h->stream));  // `un` is a stack variable
+    }
     if (n > 0) {
         WC_CUDA(cudaMemcpyAsync(h->aos, host_aos, (size_t)n * sizeof(wc_particle),
                                 cudaMemcpyHostToDevice, h->stream));
@@ -765,6 +937,7 @@ int wc_upload_particles(wc_handle* h, const wc_particle* host_aos, int32_t n) {
 }
 
 int wc_upload_sorted(wc_handle* h, const wc_particle* host_aos, int32_t n) {
+    if (h && h->slab) { int rcs = slab_sync_host(h); if (rcs) return rcs; }
     if (h && n != h->n) return fail(WC_ERR_INVALID, "n = %d differs from num_particles %d", n, h->n);
     if (h) h->nbr_valid = false;  // positions may have changed under the neighbour list
     return upload_into(h, 1, host_aos, n);
@@ -774,6 +947,7 @@ int wc_export_aos_device(wc_handle* h, int32_t which, void* device_dst) {
     if (!h || !device_dst) return fail(WC_ERR_INVALID, "NULL argument");
     if (which != 1 && which != 2) return fail(WC_ERR_INVALID, "which must be 1 or 2");
     WC_CUDA(cudaSetDevice(h->p.device));
+    { int rcs = slab_sync_host(h); if (rcs) return rcs; }
     if (h->n > 0) {
         const int first = which == 1 ? h->M : h->Cg;
         wc::k_soa_to_aos<<<div_up(h->n, 256), 256, 0, h->stream>>>(
@@ -784,8 +958,9 @@ int wc_export_aos_device(wc_handle* h, int32_t which, void* device_dst) {
 }
 
 int wc_download_particles(wc_handle* h, int32_t which, wc_particle* host_aos) {
-    if (!h || (!host_aos && h->n > 0)) return fail(WC_ERR_INVALID, "NULL argument");
-    int rc = wc_export_aos_device(h, which, h->aos);
+    if (!h) return fail(WC_ERR_INVALID, "NULL argument");
+    int rc = wc_export_aos_device(h, which, h->aos);  // (refreshes a slab handle's count first)
+    if (rc == WC_OK && !host_aos && h->n > 0) return fail(WC_ERR_INVALID, "NULL argument");
     if (rc) return rc;
     if (h->n > 0)
         WC_CUDA(cudaMemcpyAsync(host_aos, h->aos, (size_t)h->n * sizeof(wc_particle),
@@ -804,6 +979,39 @@ int wc_step(wc_handle* h, float frame_dt, const wc_step_params* sp) {
     if ((rc = run_density(h, *sp))) return rc;        // Fluid.cpp:349
     if ((rc = record(h, 4))) return rc;
     if ((rc = run_update(h, *sp, frame_dt))) return rc;  // Fluid.cpp:350
+    if ((rc = record(h, 5))) return rc;
+    h->have_times = (h->p.flags & WC_FLAG_STAGE_TIMING) != 0;
+    return WC_OK;
+}
+
+int wc_step_export(wc_handle* h, float frame_dt, const wc_step_params* sp, void* aos_dst) {
+    if (!h) return fail(WC_ERR_INVALID, "handle is NULL");
+    int rc = check_step_params(sp);
+    if (rc) return rc;
+    if (h->slab) return fail(WC_ERR_INVALID, "slab handle: use the wc_slab_* sequence");
+    if (!aos_dst && h->n > 0) return fail(WC_ERR_INVALID, "aos_dst is NULL");
+    WC_CUDA(cudaSetDevice(h->p.device));
+    // must be addressable from the device: device memory, or mapped page-locked host memory
+    float4* dst = nullptr;
+    if (h->n > 0) {
+        cudaPointerAttributes attr{};
+        const cudaError_t e = cudaPointerGetAttributes(&attr, aos_dst);
+        cudaGetLastError();
+        if (e != cudaSuccess || !attr.devicePointer ||
+            (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeHost &&
+             attr.type != cudaMemoryTypeManaged))
+            return fail(WC_ERR_INVALID, "aos_dst is not device-addressable memory");
+        dst = static_cast<float4*>(attr.devicePointer);
+    }
+    if ((rc = run_sort(h, true))) return rc;
+    if ((rc = run_density(h, *sp))) return rc;
+    if ((rc = record(h, 4))) return rc;
+    if (h->p.flags & WC_FLAG_SIMPLE_KERNELS) {  // the cross-check kernels have no fused store
+        if ((rc = run_update(h, *sp, frame_dt))) return rc;
+        if ((rc = wc_export_aos_device(h, 1, dst))) return rc;
+    } else if ((rc = run_update(h, *sp, frame_dt, dst))) {
+        return rc;
+    }
     if ((rc = record(h, 5))) return rc;
     h->have_times = (h->p.flags & WC_FLAG_STAGE_TIMING) != 0;
     return WC_OK;
@@ -887,6 +1095,7 @@ int wc_download_cells(wc_handle* h, uint32_t* cell_ids, uint32_t* counts, uint32
                       uint32_t* sorted_perm, uint32_t* neighbour_counts) {
     if (!h) return fail(WC_ERR_INVALID, "handle is NULL");
     WC_CUDA(cudaSetDevice(h->p.device));
+    { int rcs = slab_sync_host(h); if (rcs) return rcs; }
     const size_t n = (size_t)h->n;
     const size_t G2 = (size_t)h->p.grid_res * h->p.grid_res;
     // slab mode: the owned layers only (skip the ghost-low layer), offsets relative to the
@@ -918,6 +1127,7 @@ int wc_download_forces(wc_handle* h, float* forces_xyz) {
     if (!h || !forces_xyz) return fail(WC_ERR_INVALID, "NULL argument");
     if (!h->forces) return fail(WC_ERR_INVALID, "forces need WC_FLAG_DEBUG_OUTPUTS");
     WC_CUDA(cudaSetDevice(h->p.device));
+    { int rcs = slab_sync_host(h); if (rcs) return rcs; }
     const size_t n = (size_t)h->n;
     if (n == 0) return WC_OK;
     float4* tmp = (float4*)malloc(n * sizeof(float4));
@@ -940,6 +1150,11 @@ int wc_download_forces(wc_handle* h, float* forces_xyz) {
 
 int wc_device_ptrs(wc_handle* h, wc_device_view* v) {
     if (!h || !v) return fail(WC_ERR_INVALID, "NULL argument");
+    if (h->slab) {  // num_particles of a slab handle is device state: refresh the host copy
+        WC_CUDA(cudaSetDevice(h->p.device));
+        int rcs = slab_sync_host(h);
+        if (rcs) return rcs;
+    }
     for (int b = 0; b < 2; b++) {
         v->pos_rho[b] = h->pos[b];
         v->vel_pres[b] = h->vel[b];
@@ -1006,55 +1221,36 @@ int wc_slab_sort_count(wc_handle* h) {
 int wc_slab_sync_info(wc_handle* h, int32_t info[8]) {
     if (!info) return fail(WC_ERR_INVALID, "NULL argument");
     WC_NEED_SLAB(h);
-    uint32_t* hi = h->info_host;
-    int rcw = peer_wait(h, kSigLc, h->step_no);
-    if (rcw) return rcw;
-    k_collect_info<<<1, 1, 0, h->stream>>>(h->info_dev, h->lc_recv[0], h->lc_recv[1], h->errors,
-                                           h->m_in, hi);  // hi is page-locked: a direct store
-    WC_CHECK_LAUNCH(h);
-    WC_CUDA(cudaStreamSynchronize(h->stream));
+    int rc;
+    if (h->step_no == 0) return fail(WC_ERR_INVALID, "wc_slab_sync_info before the first wc_slab_sort_count");
+    if ((rc = slab_ghost_phase(h))) return rc;  // completes the record (needs the neighbours' counts)
+    h->host_stale = true;
+    if ((rc = slab_sync_host(h, false))) return rc;
+    const uint32_t* hi = h->info_host;
     for (int k = 0; k < 8; k++) info[k] = (int32_t)hi[k];
-    if ((int)hi[0] > h->cap)
+    if (hi[5] & kSlabErrOwned)
         return fail(WC_ERR_CAPACITY, "slab holds %u particles, capacity %d", hi[0], h->cap);
-    if ((int)hi[3] > h->Cg || (int)hi[4] > h->Cg)
+    if (hi[5] & kSlabErrGhost)
         return fail(WC_ERR_CAPACITY, "halo layer of %u / %u particles exceeds slab_ghost_capacity %d",
                     hi[3], hi[4], h->Cg);
-    h->n = (int)hi[0];
-    h->n_first = (int)hi[1];
-    h->n_last = (int)hi[2];
-    h->n_glow = (int)hi[3];
-    h->n_ghigh = (int)hi[4];
-    h->peer[0].n_owned = (int)hi[8];
-    h->peer[1].n_owned = (int)hi[9];
-    if (h->peer_mode() && (h->n_first > h->Cg || h->n_last > h->Cg))
+    if (hi[5] & kSlabErrHalo)
         return fail(WC_ERR_CAPACITY, "boundary layer of %d / %d particles exceeds the neighbours' "
                                      "slab_ghost_capacity %d", h->n_first, h->n_last, h->Cg);
-    h->info_valid = true;
+    if (hi[5] & kSlabErrTimeout)
+        return fail(WC_ERR_CUDA, "a neighbour's signal did not arrive (peer dead, or slab handles "
+                                 "of one process stepped out of phase order)");
     return WC_OK;
 }
 
 int wc_slab_reorder(wc_handle* h) {
     WC_NEED_SLAB(h);
-    if (!h->info_valid) return fail(WC_ERR_INVALID, "wc_slab_reorder needs wc_slab_sync_info");
-    const int G2 = h->p.grid_res * h->p.grid_res;
+    if (h->step_no == 0) return fail(WC_ERR_INVALID, "wc_slab_reorder needs wc_slab_sort_count");
+    int rc;
     // ghost layers: the neighbours' counts, scanned so the halo slices sit right before /
     // after the owned slice: [Cg - n_glow, Cg) and [Cg + n, Cg + n + n_ghigh)
-    k_install_ghost_counts<<<div_up(G2, 256), 256, 0, h->stream>>>(h->lc_recv[0], h->lc_recv[1], G2,
-                                                                  h->Lz, h->counts);
-    WC_CHECK_LAUNCH(h);
-    k_scan<<<div_up(G2, kScanTile), kScanThreads, 0, h->stream>>>(
-        h->counts, h->offsets, G2, h->scan_status_x[0], h->scan_counter_x[0],
-        (uint32_t)(h->Cg - h->n_glow));
-    WC_CHECK_LAUNCH(h);
-    k_scan<<<div_up(G2, kScanTile), kScanThreads, 0, h->stream>>>(
-        h->counts + (size_t)(h->Lz - 1) * G2, h->offsets + (size_t)(h->Lz - 1) * G2, G2,
-        h->scan_status_x[1], h->scan_counter_x[1], (uint32_t)(h->Cg + h->n));
-    WC_CHECK_LAUNCH(h);
-    // the virtual input still has the OLD owned count between the migrant slots
-    const int n_in = h->M + h->n_in_old + h->M;
-    int rc = sort_reorder_phase(h, true, n_in, h->n);
-    if (rc) return rc;
-    return peer_signal_both(h, kSigHaloPos);  // peer mode: k_reorder stored the halo remotely
+    if ((rc = slab_ghost_phase(h))) return rc;
+    // launch bounds by capacity: the virtual input [M | owned | M] and the owned region
+    return sort_reorder_phase(h, true, h->M + h->cap + h->M, h->cap);
 }
 
 int wc_slab_density(wc_handle* h, const wc_step_params* sp) {
@@ -1062,66 +1258,52 @@ int wc_slab_density(wc_handle* h, const wc_step_params* sp) {
     int rc = check_step_params(sp);
     if (rc) return rc;
     if (!h->sorted_valid) return fail(WC_ERR_INVALID, "wc_slab_density needs wc_slab_reorder");
-    if ((rc = peer_wait(h, kSigHaloPos, h->step_no))) return rc;
+    const bool simple = h->p.flags & WC_FLAG_SIMPLE_KERNELS;
+    if (simple) {  // the cross-check kernels take their sizes from the host and do not signal
+        if ((rc = slab_sync_host(h))) return rc;
+        if ((rc = slab_sync_kernel(h, kSigHaloPos, -1, -1))) return rc;
+    } else if ((rc = slab_pre_wait(h, kSigHaloPos))) {
+        return rc;
+    }
     if ((rc = run_density(h, *sp))) return rc;
-    if ((h->p.flags & WC_FLAG_SIMPLE_KERNELS) && h->peer_mode() && (rc = peer_copy_halo(h))) return rc;
-    if ((rc = peer_signal_both(h, kSigHaloRho))) return rc;  // rho, P stored remotely by the kernel
+    if (simple && h->peer_mode()) {
+        if ((rc = peer_copy_halo(h))) return rc;
+        if ((rc = slab_sync_kernel(h, -1, kSigHaloRho, kDoneDensity))) return rc;
+    }
     return record(h, 4);
 }
 
 int wc_slab_update(wc_handle* h, float frame_dt, const wc_step_params* sp) {
-    WC_NEED_SLAB(h);
-    int rc = check_step_params(sp);
-    if (rc) return rc;
-    if (!h->sorted_valid) return fail(WC_ERR_INVALID, "wc_slab_update needs wc_slab_reorder");
-    const float bin = h->d.bin_size;
-    if (!(50.0f * fabsf(frame_dt * h->p.time_scale) < bin))
-        return fail(WC_ERR_INVALID, "dt too large for one-layer migration: 50 * dt >= binSize");
-    if ((rc = peer_wait(h, kSigHaloRho, h->step_no))) return rc;
-    if ((rc = run_update(h, *sp, frame_dt))) return rc;
-    // Particles whose new z-layer left the slab: only the first / last owned layer can lose
-    // any (|v| dt < binSize), and those layers are the head / tail of the sorted order.
-    const int G = h->p.grid_res;
-    const float4* own_pos = h->pos[0] + h->M;
-    const float4* own_vel = h->vel[0] + h->M;
-    for (int dir = 0; dir < 2; dir++) {
-        const int n_layer = dir == 0 ? h->n_first : h->n_last;
-        const int start = dir == 0 ? 0 : h->n - h->n_last;
-        uint32_t* flags = h->flags + (size_t)dir * h->cap;
-        uint32_t* slots = h->slots + (size_t)dir * (h->cap + 1);
-        if (n_layer > 0) {
-            k_flag_migrants<<<div_up(n_layer, 256), 256, 0, h->stream>>>(
-                own_pos + start, n_layer, bin, G, dir == 0 ? h->z_begin : h->z_end, dir, flags);
-            WC_CHECK_LAUNCH(h);
-        }
-        const int scan_blocks = n_layer > 0 ? div_up(n_layer, kScanTile) : 1;
-        k_scan<<<scan_blocks, kScanThreads, 0, h->stream>>>(flags, slots, n_layer,
-                                                            h->scan_status_x[2 + dir],
-                                                            h->scan_counter_x[2 + dir], 0u);
-        WC_CHECK_LAUNCH(h);
-        k_pack_migrants<<<div_up(n_layer > 0 ? n_layer : 1, 256), 256, 0, h->stream>>>(
-            own_pos + start, own_vel + start, n_layer, flags, slots, h->M, h->mig_out[dir],
-            h->peer[dir].on ? h->peer[dir].mig_in : nullptr, h->errors);
-        WC_CHECK_LAUNCH(h);  // peer mode: the message went straight into the neighbour
-        if (h->peer[dir].on && (rc = peer_signal(h, dir, kSigMig))) return rc;
-    }
-    h->n_in_old = h->n;
-    if ((rc = record(h, 5))) return rc;
-    h->have_times = (h->p.flags & WC_FLAG_STAGE_TIMING) != 0;
-    return WC_OK;
+    return slab_update_impl(h, frame_dt, sp, nullptr);
 }
 
 int wc_slab_step_peer(wc_handle* h, float frame_dt, const wc_step_params* sp, int32_t info[8]) {
-    int32_t local[8];
+    return slab_step_impl(h, frame_dt, sp, info, nullptr);
+}
+
+int wc_slab_step_peer_host(wc_handle* h, float frame_dt, const wc_step_params* sp,
+                           const wc_particle* host_in, int32_t n, wc_particle* host_out,
+                           int32_t out_capacity, int32_t info[8]) {
+    if (!info) return fail(WC_ERR_INVALID, "info is NULL (the caller needs the new particle count)");
+    WC_NEED_SLAB(h);
     int rc;
-    if ((rc = wc_slab_sort_count(h))) return rc;
-    if ((rc = wc_slab_sync_info(h, info ? info : local))) return rc;
-    if ((info ? info : local)[5] != 0)
-        return fail(WC_ERR_CAPACITY, "slab capacity overflow or lost migrants (%d)",
-                    (info ? info : local)[5]);
-    if ((rc = wc_slab_reorder(h))) return rc;
-    if ((rc = wc_slab_density(h, sp))) return rc;
-    return wc_slab_update(h, frame_dt, sp);
+    if (host_in && (rc = wc_upload_particles(h, host_in, n))) return rc;
+    if (!host_out) return fail(WC_ERR_INVALID, "host_out is NULL");
+    if (out_capacity < h->cap)
+        return fail(WC_ERR_CAPACITY, "host_out holds %d particles, the slab may own %d", out_capacity,
+                    h->cap);
+    // Page-locked destination: the update kernel writes the AoS records into it directly.
+    float4* mapped = nullptr;
+    if (!(h->p.flags & WC_FLAG_SIMPLE_KERNELS)) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, host_out) == cudaSuccess &&
+            attr.type == cudaMemoryTypeHost && attr.devicePointer)
+            mapped = static_cast<float4*>(attr.devicePointer);
+        cudaGetLastError();  // an unregistered pointer is not an error here
+    }
+    if ((rc = slab_step_impl(h, frame_dt, sp, info, mapped))) return rc;  // syncs (info != NULL)
+    if (!mapped) return wc_download_particles(h, 1, host_out);
+    return WC_OK;
 }
 
 int wc_slab_ipc_export(wc_handle* h, wc_slab_ipc* out) {
@@ -1171,6 +1353,7 @@ int wc_slab_peer_open(wc_handle* h, int32_t direction, const wc_slab_ipc* peer) 
         }
         P.ipc_base[k] = mapped[k];
     }
+    if (peer->device == h->p.device) h->same_device_peer = true;
     P.pos1 = (float4*)mapped[0];
     P.vel1 = (float4*)mapped[1];
     P.mig_in = (float4*)mapped[2];
@@ -1195,6 +1378,7 @@ int wc_slab_peer_attach(wc_handle* h, int32_t direction, wc_handle* peer) {
         cudaGetLastError();
     }
     wc_handle::Peer& P = h->peer[direction];
+    if (peer->p.device == h->p.device) h->same_device_peer = true;
     P.pos1 = peer->pos[1];
     P.vel1 = peer->vel[1];
     P.mig_in = peer->mig_in[1 - direction];
@@ -1209,6 +1393,7 @@ int wc_diagnose(wc_handle* h, int32_t which, float rest_density, wc_diagnostics*
     if (which != 1 && which != 2) return fail(WC_ERR_INVALID, "which must be 1 or 2");
     if (!(rest_density > 0.0f)) return fail(WC_ERR_INVALID, "rest_density must be positive");
     WC_CUDA(cudaSetDevice(h->p.device));
+    { int rcs = slab_sync_host(h); if (rcs) return rcs; }
     if (!h->diag) {  // allocated on first use: most runs never ask
         WC_CUDA(cudaMalloc(&h->diag, (size_t)(kDiagMaxBlocks + 1) * sizeof(DiagPartial)));
         WC_CUDA(cudaMalloc(&h->diag_cells, 2 * sizeof(unsigned int)));

@@ -30,11 +30,50 @@ struct SphConsts {
     int mouse_hits;  // update.comp:118-121 evaluated on the host (all-uniform expression)
 };
 
-// Slab mode with attached neighbours (wc_slab_peer_*): where this rank's first / last owned
-// layer lives in the neighbours' buffer 2 (their ghost slots, mapped peer memory).  The kernels
-// that PRODUCE halo data store it there as they go -- the reorder writes positions and
-// velocities, the density pass adds density and pressure -- so the halo crosses NVLink under
-// the producing kernel and no copy sits between the phases.  All null / zero otherwise.
+// ---------------------------------------------------------------------------------------
+// z-slab mode (wc_slab.cuh).  Everything a step learns about itself -- how many particles the
+// slab owns after this step's sort, how many sit in its first / last layer, how many ghosts
+// the neighbours sent -- lives in this device record, written by the step's own kernels and
+// read by the later ones, so that no launch parameter depends on a host read-back and the
+// host never has to wait inside a step.
+struct SlabDyn {
+    uint32_t n;          // owned particles of the current step
+    uint32_t n_first;    // ... of them in the first owned layer (the halo sent down)
+    uint32_t n_last;     // ... in the last owned layer (the halo sent up)
+    uint32_t n_glow;     // ghost particles received from below / above
+    uint32_t n_ghigh;
+    uint32_t peer_n[2];  // the neighbours' owned counts (where this rank's halo lands there)
+    uint32_t n_in_old;   // owned count of the step's INPUT (= n of the previous step)
+    uint32_t m_in[2];    // migrants received from below / above
+    uint32_t errors;     // sticky: kSlabErr* bits
+    uint32_t pad;
+};
+enum : uint32_t {
+    kSlabErrOwned = 1u,      // more owned particles than `capacity`
+    kSlabErrGhost = 2u,      // a received halo layer exceeds slab_ghost_capacity
+    kSlabErrHalo = 4u,       // this rank's boundary layer exceeds the neighbours' ghost capacity
+    kSlabErrMigrants = 8u,   // more migrants through one face than slab_migrant_capacity
+    kSlabErrStray = 16u,     // a received migrant does not belong here (moved > 1 layer)
+    kSlabErrTimeout = 32u,   // a neighbour's signal did not arrive (dead or out-of-order peer)
+};
+
+// What a slab kernel needs beyond its own arrays; all null / zero for a whole-grid handle.
+struct SlabRef {
+    SlabDyn* dyn;
+    float4* peer_pos[2];       // the neighbours' buffer 2 (mapped peer memory): [0] below, [1] above
+    float4* peer_vel[2];
+    const uint32_t* wait[2];   // local flags the kernel waits on before it reads halo data
+    uint32_t* raise[2];        // the neighbours' flags the kernel raises once ALL its blocks are done
+    uint32_t* done;            // block counter of that kernel (zero at launch)
+    uint32_t step_no;          // the value waited for / raised
+    uint32_t Cg;               // ghost slots before the owned region of buffer 2
+    uint32_t cap;              // capacity of the owned region
+};
+
+// Where this rank's first / last owned layer lives in the neighbours' buffer 2 (their ghost
+// slots).  The kernels that PRODUCE halo data store it there as they go -- the reorder writes
+// positions and velocities, the density pass adds density and pressure -- so the halo crosses
+// NVLink under the producing kernel and no copy sits between the phases.
 struct PeerHalo {
     float4* pos[2];     // [0] = the rank below, [1] = the rank above
     float4* vel[2];
@@ -42,6 +81,71 @@ struct PeerHalo {
     uint32_t n_first;   // owned sorted particles [0, n_first) are the lower halo
     uint32_t hi_begin;  // owned sorted particles [hi_begin, n) are the upper halo
 };
+
+__device__ __forceinline__ PeerHalo peer_halo_of(const SlabRef& s) {
+    PeerHalo ph;
+    ph.pos[0] = s.peer_pos[0], ph.pos[1] = s.peer_pos[1];
+    ph.vel[0] = s.peer_vel[0], ph.vel[1] = s.peer_vel[1];
+    ph.dst[0] = ph.dst[1] = ph.n_first = ph.hi_begin = 0u;
+    if (s.dyn && (s.peer_pos[0] || s.peer_pos[1])) {
+        const SlabDyn d = *s.dyn;
+        ph.n_first = d.n_first;
+        ph.hi_begin = d.n - d.n_last;
+        // sent down: the lower neighbour's ghost-high slice, right after its owned particles;
+        // sent up: the upper neighbour's ghost-low slice, right before them
+        ph.dst[0] = s.Cg + d.peer_n[0];
+        ph.dst[1] = s.Cg - d.n_last;
+    }
+    return ph;
+}
+
+// A step that overflowed a capacity is dead: its later kernels do no work (every index they
+// would derive from the counts could leave the buffers) but still raise their signals, and the
+// host finds the sticky error word with the next info read.
+__device__ __forceinline__ bool slab_dead(const SlabRef& s) { return s.dyn && s.dyn->errors != 0u; }
+
+// ---- put-with-signal over NVLink --------------------------------------------------------
+// Block-level wait: the first two threads spin on the two local flags until the neighbours
+// raised them to step_no; bounded, so a dead or out-of-order neighbour ends in kSlabErrTimeout
+// instead of a hang.  Every thread of the block must call it.
+__device__ __forceinline__ void slab_block_wait(const SlabRef& s) {
+    if (!s.wait[0] && !s.wait[1]) return;
+    // (no indexing of s.wait by a thread-dependent value: the kernel parameter would be copied
+    // into local memory for it)
+    const uint32_t* f = threadIdx.x == 0 ? s.wait[0] : s.wait[1];
+    if (threadIdx.x < 2 && f && !(s.dyn->errors & kSlabErrTimeout)) {
+        uint32_t v = 0;
+        for (unsigned spins = 0;; spins++) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v >= s.step_no) break;
+            if (spins > (1u << 26)) {  // ~ 20 s of 300 ns naps
+                atomicOr(&s.dyn->errors, kSlabErrTimeout);
+                break;
+            }
+            __nanosleep(300);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
+// Grid-level signal: the block that finishes LAST raises the flags at both neighbours.  Every
+// thread of every block must call it, after its last store into a neighbour's memory.
+__device__ __forceinline__ void slab_grid_signal(const SlabRef& s) {
+    if (!s.done) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();  // this block's remote stores (ordered by the barrier) first
+        const uint32_t ticket = atomicAdd(s.done, 1u);
+        if (ticket == gridDim.x * gridDim.y - 1u) {
+            __threadfence_system();
+            if (s.raise[0])
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(s.raise[0]), "r"(s.step_no) : "memory");
+            if (s.raise[1])
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(s.raise[1]), "r"(s.step_no) : "memory");
+        }
+    }
+}
 
 // count.comp:32, one component: clamp(int(p / binSize), 0, gridRes - 1) with an IEEE
 // fp32 divide and truncation toward zero.  Same float-side clamp as the oracle

@@ -79,6 +79,62 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
     *reinterpret_cast<volatile unsigned long long*>(p) = v;
 }
 
+// Decoupled look-back of one tile (call with all 32 lanes of ONE warp): publishes the tile's
+// aggregate, folds the predecessors' status words and returns the tile's exclusive prefix;
+// finally publishes the inclusive prefix.  status[] must be zero at launch.
+__device__ __forceinline__ uint32_t lookback_exclusive_prefix(unsigned long long* status, int tile,
+                                                              uint32_t aggregate, int lane) {
+    uint32_t prefix = 0;
+    if (tile > 0) {
+        if (lane == 0) st_status(&status[tile], kFlagAgg | aggregate);
+        int look = tile - 1;
+        while (true) {
+            const int idx = look - lane;
+            unsigned long long s = kFlagIncl;  // virtual tile -1: inclusive prefix 0
+            if (idx >= 0) {
+                do {
+                    s = ld_status(&status[idx]);
+                } while ((s >> 32) == 0ull);
+            }
+            const unsigned incl_mask = __ballot_sync(0xffffffffu, (s >> 32) == 2ull);
+            uint32_t val = (uint32_t)s;
+            if (incl_mask) {
+                const int first = __ffs(incl_mask) - 1;
+                if (lane > first) val = 0;
+                prefix += warp_sum(val);
+                break;
+            }
+            prefix += warp_sum(val);
+            look -= 32;
+        }
+    }
+    if (lane == 0) st_status(&status[tile], kFlagIncl | (unsigned long long)(prefix + aggregate));
+    return prefix;
+}
+
+// Block-wide exclusive scan of one value per thread (kScanThreads threads); returns the
+// thread's exclusive prefix, *total = the block's sum.  s_warp: 32 words of shared memory.
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();  // s_warp may still be read from a previous call
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t w = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0u, winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+    }
+    *total = __shfl_sync(0xffffffffu, winc, 31);
+    return __shfl_sync(0xffffffffu, winc - w, warp) + (incl - v);
+}
+
 // Writes out[i] = out_base + sum(in[0..i)) for i < n and out[n] = out_base + sum(in[0..n)).
 __global__ void __launch_bounds__(kScanThreads)
 k_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n,
@@ -107,59 +163,15 @@ k_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n,
     }
     const uint32_t tsum = v[0] + v[1] + v[2] + v[3];
 
-    // block-wide exclusive scan of the per-thread sums
-    uint32_t incl = tsum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
+    uint32_t aggregate;
+    const uint32_t excl = block_exclusive_scan(tsum, s_warp, &aggregate);
     if (warp == 0) {
-        uint32_t w = s_warp[lane];
-        uint32_t winc = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
-        }
-        s_warp[lane] = winc - w;  // exclusive prefix of warp totals
-        const uint32_t aggregate = __shfl_sync(0xffffffffu, winc, 31);
-
-        // decoupled look-back (warp 0)
-        uint32_t prefix = 0;
-        if (tile > 0) {
-            if (lane == 0) st_status(&status[tile], kFlagAgg | aggregate);
-            int look = tile - 1;
-            while (true) {
-                const int idx = look - lane;
-                unsigned long long s = kFlagIncl;  // virtual tile -1: inclusive prefix 0
-                if (idx >= 0) {
-                    do {
-                        s = ld_status(&status[idx]);
-                    } while ((s >> 32) == 0ull);
-                }
-                const unsigned incl_mask = __ballot_sync(0xffffffffu, (s >> 32) == 2ull);
-                uint32_t val = (uint32_t)s;
-                if (incl_mask) {
-                    const int first = __ffs(incl_mask) - 1;
-                    if (lane > first) val = 0;
-                    prefix += warp_sum(val);
-                    break;
-                }
-                prefix += warp_sum(val);
-                look -= 32;
-            }
-        }
-        if (lane == 0) {
-            st_status(&status[tile], kFlagIncl | (unsigned long long)(prefix + aggregate));
-            s_prefix = prefix;
-        }
+        const uint32_t prefix = lookback_exclusive_prefix(status, tile, aggregate, lane);
+        if (lane == 0) s_prefix = prefix;
     }
     __syncthreads();
 
-    uint32_t run = out_base + s_prefix + s_warp[warp] + (incl - tsum);
+    uint32_t run = out_base + s_prefix + excl;
 #pragma unroll
     for (int k = 0; k < kScanItems; k++) {
         if (base + k < n) out[base + k] = run;
@@ -174,11 +186,17 @@ k_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n,
 // recorded by k_hash_count standing in for the second atomicAdd pass.
 // `base` is the index the offsets table assigns to the first sorted slot (0 unless slab
 // mode); cell id 0xFFFFFFFF marks an input slot that does not take part (slab mode).
+// slab mode: the input is the virtual array [M migrant slots | owned | M] whose owned count is
+// in the slab record (n is then only the launch bound).
 __global__ void __launch_bounds__(256)
 k_scatter_ids(const uint32_t* __restrict__ cell_ids, const uint32_t* __restrict__ ranks,
               const uint32_t* __restrict__ offsets, int n, uint32_t* __restrict__ ids,
-              uint32_t base) {
+              uint32_t base, SlabRef slab, int M) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slab.dyn) {
+        if (slab.dyn->errors) return;
+        n = M + (int)slab.dyn->n_in_old + M;
+    }
     if (i >= n) return;
     const uint32_t c = cell_ids[i];
     if (c == 0xFFFFFFFFu) return;
@@ -204,32 +222,36 @@ struct ReorderIO {
     float4* pos_out;
     float4* vel_out;
     uint32_t* perm;
-    PeerHalo peer;
 };
 
-__device__ __forceinline__ void reorder_store(const ReorderIO& io, uint32_t dst, uint32_t id,
-                                              float4 p, float4 v) {
+__device__ __forceinline__ void reorder_store(const ReorderIO& io, const PeerHalo& peer, uint32_t dst,
+                                              uint32_t id, float4 p, float4 v) {
     io.pos_out[dst] = p;
     io.vel_out[dst] = v;
     io.perm[dst] = id;
     // halo positions (+ velocities, which do not change before the update) straight into the
     // neighbours' ghost slots
-    if (io.peer.pos[0] && dst < io.peer.n_first) {
-        io.peer.pos[0][io.peer.dst[0] + dst] = p;
-        io.peer.vel[0][io.peer.dst[0] + dst] = v;
+    if (peer.pos[0] && dst < peer.n_first) {
+        peer.pos[0][peer.dst[0] + dst] = p;
+        peer.vel[0][peer.dst[0] + dst] = v;
     }
-    if (io.peer.pos[1] && dst >= io.peer.hi_begin) {
-        io.peer.pos[1][io.peer.dst[1] + (dst - io.peer.hi_begin)] = p;
-        io.peer.vel[1][io.peer.dst[1] + (dst - io.peer.hi_begin)] = v;
+    if (peer.pos[1] && dst >= peer.hi_begin) {
+        peer.pos[1][peer.dst[1] + (dst - peer.hi_begin)] = p;
+        peer.vel[1][peer.dst[1] + (dst - peer.hi_begin)] = v;
     }
 }
 
 __global__ void __launch_bounds__(256)
 k_reorder(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ offsets, int n, float bin,
-          int G, int zbase, uint32_t base, ReorderIO io, uint32_t* __restrict__ big_cells,
-          uint32_t* __restrict__ big_count, uint32_t big_cap) {
+          int G, int zbase, uint32_t base, ReorderIO io, SlabRef slab,
+          uint32_t* __restrict__ big_cells, uint32_t* __restrict__ big_count, uint32_t big_cap) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slab.dyn) {  // slab mode: n is the launch bound, the owned count is in the slab record
+        if (slab.dyn->errors) return;
+        n = (int)slab.dyn->n;
+    }
     if (j >= n) return;
+    const PeerHalo peer = peer_halo_of(slab);
     const uint32_t id = ids[j];
     const float4 p = io.pos_in[id];
     const float4 v = io.vel_in[id];  // in flight under the rank loop
@@ -244,7 +266,7 @@ k_reorder(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ offsets
     }
     uint32_t rank = 0;
     for (uint32_t k = beg; k < end; k++) rank += (ids[k] < id) ? 1u : 0u;
-    reorder_store(io, beg + rank, id, p, v);
+    reorder_store(io, peer, beg + rank, id, p, v);
 }
 
 // Cells above kBigCell (second part of k_finish_sort): one block per registered cell sorts
@@ -259,8 +281,8 @@ k_reorder(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ offsets
 __device__ __forceinline__ void
 reorder_big_cells(uint32_t* __restrict__ ids, uint32_t* __restrict__ scratch,
                   const uint32_t* __restrict__ offsets, uint32_t base, const ReorderIO& io,
-                  const uint32_t* __restrict__ big_cells, const uint32_t* __restrict__ big_count,
-                  uint32_t big_cap, int passes) {
+                  const PeerHalo& peer, const uint32_t* __restrict__ big_cells,
+                  const uint32_t* __restrict__ big_count, uint32_t big_cap, int passes) {
     __shared__ uint32_t s_bin[256];                  // running start of every digit's output range
     __shared__ uint32_t s_next[256];                 // histogram of the next pass's digit
     __shared__ uint32_t s_tot[256];
@@ -324,7 +346,7 @@ reorder_big_cells(uint32_t* __restrict__ ids, uint32_t* __restrict__ scratch,
                 __syncthreads();
                 if (valid) {
                     const uint32_t at = s_bin[d] + s_warp[warp][d] + in_warp;
-                    if (last) reorder_store(io, beg + at, id, io.pos_in[id], io.vel_in[id]);
+                    if (last) reorder_store(io, peer, beg + at, id, io.pos_in[id], io.vel_in[id]);
                     else dst[at] = id;
                 }
                 __syncthreads();

@@ -49,14 +49,6 @@ constexpr int kDensityWarps = WC_DENSITY_WARPS;  // warps (= groups) per block, 
 #ifndef WC_UPDATE_MIN_BLOCKS
 #define WC_UPDATE_MIN_BLOCKS 8
 #endif
-// 1: the replay keeps WC_REPLAY_WORDS list words resident as a sliding ring (lanes run ahead of
-// the slowest lane by up to the ring); 0 (default): hard batches of WC_REPLAY_WORDS words.  The
-// ring cuts the pair-loop iterations by a third but measured 4-15 % SLOWER on B200
-// (profiles/r01_variant_sweep.md): the pass is bound by shared-memory wavefronts of the
-// per-lane candidate loads, which the ring does not reduce.  Kept for the record / re-tuning.
-#ifndef WC_WALK_RING
-#define WC_WALK_RING 0
-#endif
 // Pair-loop iterations (two pairs each) per all-lanes-done test of the walk.
 #ifndef WC_WALK_UNROLL
 #define WC_WALK_UNROLL 1
@@ -64,14 +56,6 @@ constexpr int kDensityWarps = WC_DENSITY_WARPS;  // warps (= groups) per block, 
 // 1: drop every target's own pair from the replayed masks (it adds exactly zero force).
 #ifndef WC_DROP_SELF
 #define WC_DROP_SELF 1
-#endif
-// 1: the cull walks the nine slices as one sequence of 32-candidate chunks (see gather_group).
-#ifndef WC_CULL_CHUNKS
-#define WC_CULL_CHUNKS 0
-#endif
-// 1: the walk prefers bits whose stage slot lies in the lane's own bank group (see walk()).
-#ifndef WC_PICK_BANKS
-#define WC_PICK_BANKS 0
 #endif
 // 1: list candidates that no target of the group accepted as padding slots.
 #ifndef WC_LIST_DROP_UNUSED
@@ -150,16 +134,24 @@ __device__ __forceinline__ void build_groups_block(const uint32_t* __restrict__ 
 // Last kernel of the sort: the blocks first cut their share of the (y,z) rows into groups,
 // then sort and move the cells above kBigCell particles that k_reorder registered (none in a
 // physical scene).  One launch for both, because the second part is almost always empty.
+// Slab mode with attached neighbours: the reorder (k_reorder and the crowded cells here) has
+// stored the halo layers' positions and velocities into the neighbours, so the last block
+// raises their "halo positions" flags.
 __global__ void __launch_bounds__(kBigThreads)
 k_finish_sort(const uint32_t* __restrict__ offsets, int G, int row_begin, int row_end,
               uint4* __restrict__ groups, uint32_t* __restrict__ num_groups,
               uint32_t* __restrict__ ids, uint32_t* __restrict__ scratch, uint32_t base,
-              ReorderIO io, const uint32_t* __restrict__ big_cells,
+              ReorderIO io, SlabRef slab, const uint32_t* __restrict__ big_cells,
               const uint32_t* __restrict__ big_count, uint32_t big_cap, int passes) {
     static_assert(kGroupRows == kBigThreads, "one block shape for both parts");
-    if (groups && row_begin + (int)blockIdx.x * kGroupRows < row_end)
-        build_groups_block(offsets, G, row_begin, row_end, groups, num_groups);
-    if (ids) reorder_big_cells(ids, scratch, offsets, base, io, big_cells, big_count, big_cap, passes);
+    if (!slab_dead(slab)) {
+        if (groups && row_begin + (int)blockIdx.x * kGroupRows < row_end)
+            build_groups_block(offsets, G, row_begin, row_end, groups, num_groups);
+        if (ids)
+            reorder_big_cells(ids, scratch, offsets, base, io, peer_halo_of(slab), big_cells,
+                              big_count, big_cap, passes);
+    }
+    slab_grid_signal(slab);
 }
 
 inline int finish_sort_blocks(int rows) {
@@ -417,14 +409,6 @@ struct UpdateAcc {
         mptr = (nwb > 2) ? mptr + 256u : mend;
         const float4* abase = st.a;  // slot 0 of the word being drained
         float4 qa0 = make_float4(0, 0, 0, 0), qb0 = qa0, qa1 = qa0, qb1 = qa0;
-#if WC_PICK_BANKS
-        // A pick is two per-lane LDS.128: the eight lanes of a quarter-warp are served together
-        // and collide when two of them hit the same 16-byte bank group (slot index mod 8 = bit
-        // index mod 8) at different slots.  Every lane therefore prefers, among the bits left in
-        // its word, one whose bank group is (lane + pick number) mod 8 -- distinct within the
-        // quarter-warp -- and only falls back to the highest bit when it has none there.
-        unsigned pat = 0x01010101u << (lane & 7);
-#endif
         auto pick = [&](float4& qa, float4& qb) -> bool {
             if (m == 0u) {
                 m = mn;
@@ -433,13 +417,7 @@ struct UpdateAcc {
                 mptr = (mptr == mend) ? mend : mptr + 128u;
             }
             const bool on = m != 0u;
-#if WC_PICK_BANKS
-            const unsigned pref = m & pat;
-            pat = __funnelshift_l(pat, pat, 1);
-            const unsigned hb = highest_bit(pref ? pref : m);
-#else
             const unsigned hb = highest_bit(m);  // 0xffffffff when no bit is left
-#endif
             if (on) {
                 const float4* q = abase + hb;
                 qa = q[0];
@@ -447,11 +425,7 @@ struct UpdateAcc {
             } else {
                 qa.w = 0.0f;  // see pair()
             }
-#if WC_PICK_BANKS
-            m &= ~(on ? (1u << hb) : 0u);
-#else
             m &= bits_below(hb);  // drops bit hb (m stays 0 when it was 0)
-#endif
             return on;
         };
         while (__any_sync(0xffffffffu, (m | mn) != 0u || mptr != mend)) {
@@ -486,126 +460,6 @@ struct UpdateAcc {
         walk(st, nw, c, p, v);
     }
 };
-
-// ---------------------------------------------------------------------------------------
-// Ring replay of a group's neighbour list (update pass).  With hard batches every lane waits at
-// each batch's end for the lane with the most accepted bits in that batch (tests/model/model_walk.py:
-// 41 pair-loop iterations per group at 5 words against 25 for the whole list at once).  Here
-// the stage holds the R = kReplayWords most recent list words as a ring: a lane drains its own
-// bits word after word and may run ahead of the slowest lane by the resident window; once every
-// lane has left the oldest word its slot is refilled with the next list word (candidate gathers
-// issued before the iteration's pair math, stored after it).  Same pairs, same per-lane order
-// as the batched walk, so the sums are bit-identical to it.
-__device__ __forceinline__ void replay_ring(UpdateStage& st, UpdateAcc& acc,
-                                            const uint32_t* __restrict__ widx,
-                                            const uint32_t* __restrict__ wmask, int nw,
-                                            uint32_t first_target,
-                                            const float4* __restrict__ pos_rho,
-                                            const float4* __restrict__ vel_pres,
-                                            const SphConsts& c, float4 p, float4 v) {
-    constexpr int R = kReplayWords;
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    {   // fill the ring with words [0, min(R, nw))
-        uint32_t jj[R];
-#pragma unroll
-        for (int u = 0; u < R; u++) {
-            jj[u] = kNoIndex;
-            uint32_t mk = 0u;
-            if (u < nw) {
-                jj[u] = widx[(size_t)u * 32];
-                mk = wmask[(size_t)u * 32];
-            }
-            st.mask[u * 32 + lane] = mk;
-        }
-#pragma unroll
-        for (int u = 0; u < R; u++) {
-            if (jj[u] != kNoIndex) {
-                float4 qa = pos_rho[jj[u]];
-                qa.w = __frcp_rn(qa.w);
-                st.a[u * 32 + lane] = qa;
-                st.b[u * 32 + lane] = vel_pres[jj[u]];
-            }
-        }
-        __syncwarp();
-        // a listed candidate that is one of this group's own targets: drop that target's self
-        // pair (it would add exactly zero; this only saves the evaluation)
-#pragma unroll
-        for (int u = 0; u < R; u++) {
-            const uint32_t t = jj[u] - first_target;
-            if (t < 32u) atomicAnd(&st.mask[u * 32 + t], ~(1u << lane));
-        }
-        __syncwarp();
-    }
-    // warp-uniform ring state: resident words are [base, horizon), word w sits in slot w % R
-    int base = 0, bslot = 0, horizon = min(nw, R);
-    uint32_t jn = kNoIndex, mkn = 0u;  // index / mask word of the next refill, prefetched
-    if (R < nw) {
-        jn = widx[(size_t)R * 32];
-        mkn = wmask[(size_t)R * 32];
-    }
-    // per-lane walk state
-    int wl = 0, slot = 0;              // the word this lane is draining, and its slot
-    unsigned m = st.mask[lane];
-    float4 qa0 = make_float4(0, 0, 0, 0), qb0 = qa0, qa1 = qa0, qb1 = qa0;
-    auto pick = [&](float4& qa, float4& qb) -> bool {
-        if (m == 0u && wl + 1 < horizon) {
-            wl++;
-            slot = (slot + 1 == R) ? 0 : slot + 1;
-            m = st.mask[slot * 32 + lane];
-        }
-        const bool on = m != 0u;
-        const unsigned hb = highest_bit(m);  // 0xffffffff when no bit is left
-        if (on) {
-            const float4* q = st.a + slot * 32 + hb;
-            qa = q[0];
-            qb = q[kReplaySlots];
-        } else {
-            qa.w = 0.0f;  // see UpdateAcc::pair()
-        }
-        m &= bits_below(hb);
-        return on;
-    };
-    for (;;) {
-        // the oldest word any lane still needs
-        const int wmin = __reduce_min_sync(full, (m != 0u) ? wl : wl + 1);
-        if (wmin >= nw) break;
-        const bool retire = base < wmin;            // every lane has left word `base`
-        const bool refill = retire && base + R < nw;
-        float4 qan = make_float4(0, 0, 0, 0), qbn = qan;
-        if (refill && jn != kNoIndex) {
-            qan = pos_rho[jn];
-            qbn = vel_pres[jn];
-        }
-        const bool on0 = pick(qa0, qb0);
-        const bool on1 = pick(qa1, qb1);
-        acc.pair(c, p, v, qa0, qb0, on0);
-        acc.pair(c, p, v, qa1, qb1, on1);
-        if (retire) {
-            if (refill) {
-                st.mask[bslot * 32 + lane] = mkn;
-                if (jn != kNoIndex) {
-                    qan.w = __frcp_rn(qan.w);
-                    st.a[bslot * 32 + lane] = qan;
-                    st.b[bslot * 32 + lane] = qbn;
-                }
-                __syncwarp();
-                const uint32_t t = jn - first_target;
-                if (t < 32u) atomicAnd(&st.mask[bslot * 32 + t], ~(1u << lane));
-                __syncwarp();
-                const int wn = base + R + 1;
-                jn = kNoIndex, mkn = 0u;
-                if (wn < nw) {
-                    jn = widx[(size_t)wn * 32];
-                    mkn = wmask[(size_t)wn * 32];
-                }
-            }
-            base++;
-            bslot = (bslot + 1 == R) ? 0 : bslot + 1;
-            horizon = min(nw, base + R);
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------
 // The shared gather driver: phase 1 (cull + stage) and the hand-over to acc.process().
@@ -646,62 +500,6 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
     }
     constexpr int kDepth = Stage::kDepth;
     int cnt = 0, head = 0;  // pending candidates are stage[head, head + cnt) (mod ring)
-#if WC_CULL_CHUNKS
-    // The nine slices are walked as ONE sequence of 32-candidate chunks (warp-uniform cursor:
-    // slice number, position, end), kDepth chunks in flight per lane, so a slice costs
-    // ceil(len / 32) cull steps and never a mostly-empty kDepth x 32 block of its own.
-    int sl = -1;
-    uint32_t cur = 0, cend = 0;
-    for (bool more = true; more;) {
-        uint32_t cb[kDepth], ce[kDepth];
-#pragma unroll
-        for (int k = 0; k < kDepth; k++) {
-            while (cur >= cend && sl < 9) {
-                sl++;
-                cur = __shfl_sync(full, sbeg, sl & 15);
-                cend = sl < 9 ? __shfl_sync(full, send, sl & 15) : 0u;
-            }
-            if (sl >= 9) {
-                cb[k] = ce[k] = 0u;  // no chunk: every lane fails the index test
-                more = false;
-            } else {
-                cb[k] = cur, ce[k] = cend;
-                cur += 32u;
-            }
-        }
-        // The loads are unconditional: a slice's last chunk reads up to 31 entries past its
-        // end (the arrays carry kCullOverread slack); those lanes fail the index test.
-        float4 q[kDepth];
-#pragma unroll
-        for (int k = 0; k < kDepth; k++) q[k] = pos_rho[cb[k] + lane];
-#pragma unroll
-        for (int k = 0; k < kDepth; k++) {
-            const uint32_t j = cb[k] + lane;
-            const float ex = fmaxf(fmaxf(bx0 - q[k].x, q[k].x - bx1), 0.0f);
-            const float ey = fmaxf(fmaxf(by0 - q[k].y, q[k].y - by1), 0.0f);
-            const float ez = fmaxf(fmaxf(bz0 - q[k].z, q[k].z - bz1), 0.0f);
-            const bool keep = j < ce[k] && ex * ex + ey * ey + ez * ez < Tcull;
-            const unsigned km = __ballot_sync(full, keep);
-            if (keep) {
-                const int at = cnt + __popc(km & lt);
-                st.put(Stage::kWrap ? ((head + at) & Stage::kWrap) : at, q[k], j, vel_pres);
-            }
-            cnt += __popc(km);
-        }
-        if (cnt >= Stage::kBatch) {
-            __syncwarp();
-            acc.process(st, head, Stage::kBatch, c, p, v, Teff);
-            __syncwarp();
-            cnt -= Stage::kBatch;
-            if constexpr (Stage::kWrap != 0) {
-                head ^= Stage::kBatch;  // the ring's other half
-            } else if (cnt > 0) {  // linear stage: move the (< 32) leftovers to the front
-                st.move(lane, Stage::kBatch + lane, lane < cnt);
-                __syncwarp();
-            }
-        }
-    }
-#else
     for (int s = 0; s < 9; s++) {
         const uint32_t end = __shfl_sync(full, send, s);
         for (uint32_t j0 = __shfl_sync(full, sbeg, s); j0 < end; j0 += 32 * kDepth) {
@@ -742,7 +540,6 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
             }
         }
     }
-#endif
     if (cnt > 0) {  // final partial batch: pad to a multiple of 32
         const int count = (cnt + 31) & ~31;
         if (cnt + lane < count) st.pad(head + cnt + lane);
@@ -794,12 +591,13 @@ __device__ __forceinline__ GroupCtx group_prologue(const float4* pos_rho, const 
 }
 
 template <bool kDebug>
-__global__ void __launch_bounds__(kDensityWarps * 32, WC_DENSITY_MIN_BLOCKS)
-k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
-               const uint32_t* __restrict__ offsets, SphConsts c,
-               const uint4* __restrict__ groups, const uint32_t* __restrict__ num_groups,
-               uint32_t* __restrict__ neighbour_counts, NbrList list, PeerHalo peer) {
-    __shared__ DensityStage s_stage[kDensityWarps];
+__device__ __forceinline__ void density_group(float4* pos_rho, float4* __restrict__ vel_pres,
+                                              const uint32_t* __restrict__ offsets,
+                                              const SphConsts& c, const uint4* __restrict__ groups,
+                                              const uint32_t* __restrict__ num_groups,
+                                              uint32_t* __restrict__ neighbour_counts,
+                                              const NbrList& list, const SlabRef& slab,
+                                              DensityStage& stage) {
     const int lane = threadIdx.x & 31;
     float4 p;
     const GroupCtx x = group_prologue(pos_rho, c, groups, num_groups, kDensityWarps, &p);
@@ -810,12 +608,13 @@ k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
         acc.mask_out = list.mask + (size_t)x.g * list.cap_words * 32 + lane;
         acc.cap_words = list.cap_words;
     }
-    gather_group(pos_rho, vel_pres, offsets, c, s_stage[threadIdx.x >> 5], acc, x.valid,
-                 x.gg, p, make_float4(0, 0, 0, 0));
+    gather_group(pos_rho, vel_pres, offsets, c, stage, acc, x.valid, x.gg, p,
+                 make_float4(0, 0, 0, 0));
     if (list.idx && lane == 0) list.words[x.g] = acc.overflow ? kListOverflow : acc.words_used;
     if (!x.valid) return;
     float rho, pres;
     finish_density(c, acc.sum0 + acc.sum1, p.x, p.y, p.z, &rho, &pres);
+    const PeerHalo peer = peer_halo_of(slab);
     // In place like density.comp:135; the gather only reads x,y,z, which do not change.
     reinterpret_cast<float*>(pos_rho)[4 * (size_t)x.i + 3] = rho;
     reinterpret_cast<float*>(vel_pres)[4 * (size_t)x.i + 3] = pres;
@@ -836,6 +635,24 @@ k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
     }
 }
 
+// density.comp:81-137, one warp per group.  Slab mode with attached neighbours: the block
+// first waits for the neighbours' halo positions (stored into this rank's ghost slots by
+// their reorder), and the block that finishes last tells them that this rank's halo density /
+// pressure is in their ghost copies.
+template <bool kDebug>
+__global__ void __launch_bounds__(kDensityWarps * 32, WC_DENSITY_MIN_BLOCKS)
+k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
+               const uint32_t* __restrict__ offsets, SphConsts c,
+               const uint4* __restrict__ groups, const uint32_t* __restrict__ num_groups,
+               uint32_t* __restrict__ neighbour_counts, NbrList list, SlabRef slab) {
+    __shared__ DensityStage s_stage[kDensityWarps];
+    slab_block_wait(slab);
+    if (!slab_dead(slab))
+        density_group<kDebug>(pos_rho, vel_pres, offsets, c, groups, num_groups, neighbour_counts,
+                              list, slab, s_stage[threadIdx.x >> 5]);
+    slab_grid_signal(slab);
+}
+
 // update.comp:134-232.  With a valid neighbour list the warp replays the density pass's
 // words; without one (list.idx == nullptr, or this group overflowed its list) it runs the
 // cull + distance test itself.
@@ -845,9 +662,13 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
               const uint32_t* __restrict__ offsets, SphConsts c,
               const uint4* __restrict__ groups, const uint32_t* __restrict__ num_groups,
               float4* __restrict__ pos_out, float4* __restrict__ vel_out,
-              float4* __restrict__ forces, NbrList list, float4* __restrict__ aos_out) {
+              float4* __restrict__ forces, NbrList list, float4* __restrict__ aos_out,
+              SlabRef slab) {
     extern __shared__ __align__(16) unsigned char s_dyn[];  // kUpdateWarps stages (may exceed 48 KB)
     UpdateStage* s_stage = reinterpret_cast<UpdateStage*>(s_dyn);
+    // slab mode with attached neighbours: the ghosts' density / pressure must have arrived
+    slab_block_wait(slab);
+    if (slab_dead(slab)) return;
     const int lane = threadIdx.x & 31;
     float4 p;
     const GroupCtx x = group_prologue(pos_rho, c, groups, num_groups, kUpdateWarps, &p);
@@ -864,10 +685,6 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
         const uint32_t* widx = list.idx + (size_t)x.g * list.cap_words * 32 + lane;
         const uint32_t* wmask = list.mask + (size_t)x.g * list.cap_words * 32 + lane;
         const uint32_t first_target = (uint32_t)(x.i - lane);
-#if WC_WALK_RING
-        replay_ring(st, acc, widx, wmask, (int)nw, first_target, pos_rho, vel_pres, c, p, v);
-    }
-#else
         st.init(lane);
         for (uint32_t w0 = 0; w0 < nw; w0 += kReplayWords) {
             uint32_t jj[kReplayWords];
@@ -905,7 +722,6 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
             __syncwarp();
         }
     }
-#endif
     if (!x.valid) return;
     const float kp = -0.5f * (c.m * c.spikyC), kv = c.m * c.viscC;
     float4 po, vo, fo;
@@ -935,7 +751,7 @@ inline int blocks_for(int groups, int warps) { return (groups + warps - 1) / war
 inline void launch_density_tile(float4* pos_rho, float4* vel_pres, const uint32_t* offsets,
                                 const SphConsts& c, const GroupTable& gt,
                                 uint32_t* neighbour_counts, NbrList list, cudaStream_t stream,
-                                const PeerHalo& peer = PeerHalo{}) {
+                                const SlabRef& peer = SlabRef{}) {
     const int blocks = blocks_for(gt.max_groups, kDensityWarps);
     if (neighbour_counts)
         k_density_tile<true><<<blocks, kDensityWarps * 32, 0, stream>>>(
@@ -948,7 +764,8 @@ inline void launch_density_tile(float4* pos_rho, float4* vel_pres, const uint32_
 inline void launch_update_tile(const float4* pos_rho, const float4* vel_pres,
                                const uint32_t* offsets, const SphConsts& c, const GroupTable& gt,
                                float4* pos_out, float4* vel_out, float4* forces, NbrList list,
-                               cudaStream_t stream, float4* aos_out = nullptr) {
+                               cudaStream_t stream, float4* aos_out = nullptr,
+                               const SlabRef& slab = SlabRef{}) {
     const int blocks = blocks_for(gt.max_groups, kUpdateWarps);
     constexpr size_t smem = kUpdateWarps * sizeof(UpdateStage);
     if (smem > 48 * 1024) {  // opt-in size; the attribute is per device, so set it per launch
@@ -960,11 +777,11 @@ inline void launch_update_tile(const float4* pos_rho, const float4* vel_pres,
     if (forces)
         k_update_tile<true><<<blocks, kUpdateWarps * 32, smem, stream>>>(
             pos_rho, vel_pres, offsets, c, gt.groups, gt.count, pos_out, vel_out, forces,
-            list, aos_out);
+            list, aos_out, slab);
     else
         k_update_tile<false><<<blocks, kUpdateWarps * 32, smem, stream>>>(
             pos_rho, vel_pres, offsets, c, gt.groups, gt.count, pos_out, vel_out, nullptr,
-            list, aos_out);
+            list, aos_out, slab);
 }
 
 }  // namespace wc

@@ -39,7 +39,14 @@ public:
     FluidRef particleRadius(float r);
     FluidRef position(vec3 p);
     FluidRef renderMode(int m);
-    FluidRef device(int ordinal);            // new: CUDA device ordinal
+    FluidRef device(int ordinal);            // new: CUDA device ordinal (the first one used)
+    // new: decompose the fluid into n z-slabs, one per device device()..device()+n-1 of this
+    // box: equal-count cuts from the initial particles, the neighbours attached
+    // through peer memory, every update() queued on all of them by this one host thread with
+    // no wait inside a step.  The particle-buffer surface stays: buffer 1 read back is the
+    // slabs in z order = the whole-grid array, bit-identical to the single-device run.  With
+    // fewer devices than slabs the slabs share devices round-robin (a test configuration).
+    FluidRef devices(int n);
     FluidRef seed(uint32_t s);               // new: seed of the portable jitter generator (Q16)
     // Per-step mutable (GUI-bound in the reference).
     FluidRef viscosityCoefficient(float c);
@@ -63,10 +70,12 @@ public:
 
     // The particle-buffer surface: buffer 1 = current state (what the renderer binds,
     // Fluid.cpp:394), buffer 2 = cell-sorted input of the last step with density / pressure.
-    Buffer particleBuffer1() const { return Buffer{handle_, BufferKind::Particles1}; }
-    Buffer particleBuffer2() const { return Buffer{handle_, BufferKind::Particles2}; }
-    SortRef sort() const { return sort_; }
+    Buffer particleBuffer1() const { return buffer(BufferKind::Particles1); }
+    Buffer particleBuffer2() const { return buffer(BufferKind::Particles2); }
+    SortRef sort() const { return sort_; }  // single device only (null for a decomposed fluid)
     wc_handle* nativeHandle() const { return handle_; }
+    const std::vector<wc_handle*>& slabHandles() const { return slabs_; }  // empty: single device
+    const std::vector<int>& slabCuts() const { return cuts_; }             // z-layer cuts [0..G]
 
     // Checkpoint / resume: the state of buffer 1 with the setup-time parameters.
     // restoreCheckpoint() configures the object from the file and calls setup(); the run then
@@ -94,8 +103,17 @@ protected:
     void runDensityProg(Buffer particle_buffer);                              // Fluid.cpp:268
     void runUpdateProg(Buffer in_particles, Buffer out_particles, float time_step);  // :294
     wc_step_params stepParams() const;
+    Buffer buffer(BufferKind kind) const {
+        Buffer b{handle_, kind};
+        if (!slabs_.empty()) b.slabs = &slabs_;
+        return b;
+    }
+    void setupSlabs();   // the decomposed counterpart of setup()'s buffer creation
+    void destroyHandles();
 
-    int num_particles_, grid_res_, render_mode_, device_;
+    int num_particles_, grid_res_, render_mode_, device_, num_devices_;
+    std::vector<wc_handle*> slabs_;  // z order; handle_ == slabs_[0] when decomposed
+    std::vector<int> cuts_;
     uint32_t seed_;
     float size_, particle_radius_, viscosity_coefficient_, stiffness_, rest_density_,
         rest_pressure_, gravity_strength_, time_scale_;

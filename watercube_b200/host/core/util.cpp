@@ -28,6 +28,18 @@ std::vector<Particle> getParticles(Buffer buffer, int num_items) {
     wc_handle* h = need(buffer, "getParticles");
     if (buffer.kind != BufferKind::Particles1 && buffer.kind != BufferKind::Particles2)
         throw Error(WC_ERR_INVALID, "getParticles: not a particle buffer");
+    if (buffer.slabs) {  // decomposed fluid: the slabs in z order
+        std::vector<Particle> all;
+        for (wc_handle* s : *buffer.slabs) {
+            wc_device_view view;
+            check(wc_device_ptrs(s, &view));  // (waits for the slab's queued steps)
+            const size_t at = all.size();
+            all.resize(at + (size_t)view.num_particles);
+            check(wc_download_particles(s, (int)buffer.kind, reinterpret_cast<wc_particle*>(all.data() + at)));
+        }
+        if (num_items >= 0 && (size_t)num_items < all.size()) all.resize((size_t)num_items);
+        return all;
+    }
     wc_device_view view;
     check(wc_device_ptrs(h, &view));
     std::vector<Particle> all((size_t)view.num_particles);
@@ -38,6 +50,9 @@ std::vector<Particle> getParticles(Buffer buffer, int num_items) {
 
 void setParticles(Buffer buffer, const std::vector<Particle>& particles) {
     wc_handle* h = need(buffer, "setParticles");
+    if (buffer.slabs)
+        throw Error(WC_ERR_INVALID, "setParticles: a decomposed fluid takes new particles through "
+                                    "Fluid::initialParticles (they must be cut into slabs)");
     const wc_particle* src = reinterpret_cast<const wc_particle*>(particles.data());
     if (buffer.kind == BufferKind::Particles1)
         check(wc_upload_particles(h, src, (int32_t)particles.size()));
@@ -49,6 +64,9 @@ void setParticles(Buffer buffer, const std::vector<Particle>& particles) {
 
 std::vector<uint32_t> getUints(Buffer buffer, int num_items) {
     wc_handle* h = need(buffer, "getUints");
+    if (buffer.slabs)
+        throw Error(WC_ERR_INVALID, "getUints: the cell tables of a decomposed fluid are per slab "
+                                    "(Fluid::slabHandles + wc_download_cells)");
     wc_device_view view;
     check(wc_device_ptrs(h, &view));
     wc_derived d;
@@ -87,7 +105,7 @@ void saveCheckpoint(const std::string& path, const CheckpointHeader& header,
                     const std::vector<Particle>& particles) {
     CheckpointHeader h = header;
     std::memcpy(h.magic, kMagic, sizeof(kMagic));
-    h.version = 1;
+    h.version = 2;
     h.num_particles = (int32_t)particles.size();
     FILE* f = std::fopen(path.c_str(), "wb");
     const bool ok = f && std::fwrite(&h, sizeof(h), 1, f) == 1 &&
@@ -100,17 +118,28 @@ void saveCheckpoint(const std::string& path, const CheckpointHeader& header,
 std::vector<Particle> loadCheckpoint(const std::string& path, CheckpointHeader* header) {
     FILE* f = std::fopen(path.c_str(), "rb");
     if (!f) throw Error(WC_ERR_INVALID, "loadCheckpoint: cannot open " + path);
-    CheckpointHeader h;
+    CheckpointHeader h = CheckpointHeader();
     std::vector<Particle> particles;
-    bool ok = std::fread(&h, sizeof(h), 1, f) == 1 && std::memcmp(h.magic, kMagic, sizeof(kMagic)) == 0 &&
-              h.version == 1 && h.num_particles >= 0;
+    // the file length is checked against the header BEFORE anything is allocated from it
+    long long file_bytes = -1;
+    if (std::fseek(f, 0, SEEK_END) == 0) file_bytes = (long long)std::ftell(f);
+    std::rewind(f);
+    bool ok = file_bytes >= (long long)kCheckpointHeaderV1Bytes &&
+              std::fread(&h, kCheckpointHeaderV1Bytes, 1, f) == 1 &&
+              std::memcmp(h.magic, kMagic, sizeof(kMagic)) == 0 &&
+              (h.version == 1 || h.version == 2) && h.num_particles >= 0;
+    const size_t header_bytes = h.version == 2 ? sizeof(CheckpointHeader) : kCheckpointHeaderV1Bytes;
+    ok = ok && file_bytes == (long long)header_bytes + (long long)h.num_particles * (long long)sizeof(Particle);
+    if (ok && h.version == 2)
+        ok = std::fread(reinterpret_cast<char*>(&h) + kCheckpointHeaderV1Bytes,
+                        sizeof(CheckpointHeader) - kCheckpointHeaderV1Bytes, 1, f) == 1;
     if (ok) {
         particles.resize((size_t)h.num_particles);
-        ok = std::fread(particles.data(), sizeof(Particle), particles.size(), f) == particles.size() &&
-             std::fgetc(f) == EOF;  // a truncated or over-long file is not a checkpoint
+        ok = particles.empty() ||
+             std::fread(particles.data(), sizeof(Particle), particles.size(), f) == particles.size();
     }
     std::fclose(f);
-    if (!ok) throw Error(WC_ERR_INVALID, "loadCheckpoint: " + path + " is not a version-1 checkpoint");
+    if (!ok) throw Error(WC_ERR_INVALID, "loadCheckpoint: " + path + " is not a checkpoint (bad magic, version or length)");
     if (header) *header = h;
     return particles;
 }

@@ -64,6 +64,10 @@ enum class BufferKind : int {
 struct Buffer {
     wc_handle* handle = nullptr;
     BufferKind kind = BufferKind::None;
+    // A fluid decomposed over several devices (Fluid::devices): the z-slabs' handles in z
+    // order; `handle` is then the first of them.  Reading such a buffer concatenates the
+    // slabs, which IS the whole-grid array in the whole-grid order.
+    const std::vector<wc_handle*>* slabs = nullptr;
     explicit operator bool() const { return handle != nullptr && kind != BufferKind::None; }
 };
 
@@ -87,13 +91,15 @@ std::vector<uint32_t> getUints(Buffer buffer, int num_items);             // uti
 // util.cpp:113-126: position, velocity, density, pressure, ivec3(position / binSize).
 void printParticles(Buffer particle_buffer, int n, float bin_size);
 
-// Checkpoint file: a 64-byte header followed by the 32-byte AoS records exactly as
-// getParticles returns them (util.cpp:42-63 layout), so `numpy.fromfile(f, float32,
-// offset=64).reshape(-1, 8)` reads it.  Buffer 1 keeps its order across save / restore, so a
-// restored run continues bit-identically (the stable sort only sees positions and order).
+// Checkpoint file (version 2): a 160-byte header followed by the 32-byte AoS records exactly
+// as getParticles returns them (util.cpp:42-63 layout), so `numpy.fromfile(f, float32,
+// offset=160).reshape(-1, 8)` reads it.  Buffer 1 keeps its order across save / restore and the
+// header carries every setup-time AND per-step parameter, so a restored run continues
+// bit-identically without the caller re-applying anything (the stable sort only sees
+// positions and order).  Version-1 files (64-byte header, no step parameters) still load.
 struct CheckpointHeader {
     char magic[8];          // "WCB200\0\0"
-    uint32_t version;       // 1
+    uint32_t version;       // 2
     int32_t num_particles;
     int32_t grid_res;
     float size;
@@ -102,8 +108,17 @@ struct CheckpointHeader {
     uint64_t steps;         // Fluid::update calls that produced this state
     double time;            // sum of the frame times passed to update()
     uint8_t reserved[16];
+    // ---- version 2: the wc_step_params inputs (Fluid.cpp:15-21) and the mouse ray
+    float viscosity_coefficient, stiffness, rest_density, rest_pressure;
+    float gravity_strength;
+    float gravity_direction[3];
+    float position[3];      // Fluid::position_, which the mouse ray is relative to
+    int32_t has_mouse_ray;
+    float mouse_origin[3], mouse_dir[3];
+    uint8_t reserved2[24];
 };
-static_assert(sizeof(CheckpointHeader) == 64, "checkpoint header is 64 bytes");
+static_assert(sizeof(CheckpointHeader) == 160, "checkpoint header is 160 bytes");
+constexpr size_t kCheckpointHeaderV1Bytes = 64;
 
 void saveCheckpoint(const std::string& path, const CheckpointHeader& header,
                     const std::vector<Particle>& particles);

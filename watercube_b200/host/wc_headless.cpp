@@ -3,6 +3,9 @@
 // time (quirk Q15: the app uses the wall clock), print conserved / statistical quantities.
 //
 //   wc_headless [--particles N] [--size S] [--grid G] [--steps K] [--device D] [--dump file]
+//               [--gpus N]         z-slab decomposition over N devices of this box, driven by this
+//                                  one process and thread (core::Fluid::devices); same results
+//               [--stiffness K] [--viscosity MU] [--rest-density R]   per-step parameters
 //               [--initial-only]   (write the initial lattice to --dump; no device needed)
 //               [--checkpoint file]  write a resumable checkpoint (header + AoS) after the run
 //               [--restore file]     start from a checkpoint instead of the initial lattice
@@ -24,8 +27,8 @@
 using namespace core;
 
 int main(int argc, char** argv) {
-    int n = 80000, grid = 21, steps = 100, device = 0;
-    float size = 1.0f;
+    int n = 80000, grid = 21, steps = 100, device = 0, gpus = 1;
+    float size = 1.0f, stiffness = -1.0f, viscosity = -1.0f, rest_density = -1.0f;
     const char* dump = nullptr;
     const char* checkpoint = nullptr;
     const char* restore = nullptr;
@@ -41,6 +44,10 @@ int main(int argc, char** argv) {
         else if (const char* v = next("--grid")) grid = std::atoi(v);
         else if (const char* v = next("--steps")) steps = std::atoi(v);
         else if (const char* v = next("--device")) device = std::atoi(v);
+        else if (const char* v = next("--gpus")) gpus = std::atoi(v);
+        else if (const char* v = next("--stiffness")) stiffness = (float)std::atof(v);
+        else if (const char* v = next("--viscosity")) viscosity = (float)std::atof(v);
+        else if (const char* v = next("--rest-density")) rest_density = (float)std::atof(v);
         else if (const char* v = next("--dump")) dump = v;
         else if (const char* v = next("--checkpoint")) checkpoint = v;
         else if (const char* v = next("--restore")) restore = v;
@@ -48,7 +55,10 @@ int main(int argc, char** argv) {
         else { std::fprintf(stderr, "unknown argument %s\n", argv[i]); return 1; }
     }
     try {
-        FluidRef fluid = Fluid::create("fluid")->numParticles(n)->size(size)->gridRes(grid)->device(device);
+        FluidRef fluid = Fluid::create("fluid")->numParticles(n)->size(size)->gridRes(grid)->device(device)->devices(gpus);
+        if (stiffness >= 0) fluid->stiffness(stiffness);
+        if (viscosity >= 0) fluid->viscosityCoefficient(viscosity);
+        if (rest_density >= 0) fluid->restDensity(rest_density);
         if (initial_only) {
             const std::vector<Particle>& init = fluid->initialParticles();
             FILE* f = dump ? std::fopen(dump, "wb") : nullptr;

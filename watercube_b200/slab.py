@@ -221,11 +221,12 @@ def attach_peers_local(backends: Sequence["CudaSlabBackend"]):
                 b.clear_recv(d)
 
 
-def run_step_peer(backend, frame_dt: float):
+def run_step_peer(backend, frame_dt: float, wait: bool = True):
     """One step of one rank in peer-memory mode (every rank runs this; no host exchange): the
-    five phases as ONE C-ABI call, wc_slab_step_peer."""
+    five phases as ONE C-ABI call, wc_slab_step_peer.  wait=False only queues the step -- the
+    host does not wait anywhere in it; capacity errors then surface at the next info read."""
     if hasattr(backend, "fluid"):
-        backend.info = backend.fluid.slab_step_peer(frame_dt)   # raises on capacity errors
+        backend.info = backend.fluid.slab_step_peer(frame_dt, wait=wait)  # raises on errors
         return
     backend.sort_count()
     info = backend.sync_info()
@@ -234,6 +235,16 @@ def run_step_peer(backend, frame_dt: float):
     backend.reorder()
     backend.density()
     backend.update(frame_dt)
+
+
+def run_steps_peer_async(backends: Sequence["CudaSlabBackend"], frame_dt: float, steps: int = 1):
+    """Several slab handles driven by ONE host thread (virtual ranks, or one process driving
+    every GPU of the box): whole steps are queued handle after handle -- nothing in a step waits
+    for the host, and a kernel that waits for a neighbour's signal only ever waits for work that
+    is already queued or will be queued without anybody waiting for it."""
+    for _ in range(steps):
+        for b in backends:
+            b.fluid.slab_step_peer(frame_dt, wait=False)
 
 
 def run_step_peer_local(backends: Sequence["CudaSlabBackend"], frame_dt: float):
@@ -308,6 +319,11 @@ class CudaSlabBackend:
 
         self.torch = torch
         self.device = torch.device("cuda", device)
+        if stream is None:
+            # run_step() issues the NCCL sends / receives on torch's current stream against
+            # buffers the wc_slab_* kernels produce and consume: both must be ONE stream (a
+            # private library stream would leave the two unordered)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
         self.fluid = capi.Fluid(num_particles=0, capacity=capacity, device=device, flags=flags,
                                 stream=stream,
                                 slab=(z_begin, z_end, ghost_capacity, migrant_capacity),

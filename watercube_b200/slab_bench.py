@@ -162,7 +162,7 @@ def run(args, rank, world, local):
 
     def one_step():
         if peer:
-            slab.run_step_peer(b, FRAME_DT)
+            slab.run_step_peer(b, FRAME_DT, wait=False)   # queued only: no host wait in a step
         else:
             slab.run_step(drv, FRAME_DT)
 
