@@ -105,39 +105,54 @@ __device__ __forceinline__ PeerHalo peer_halo_of(const SlabRef& s) {
 __device__ __forceinline__ bool slab_dead(const SlabRef& s) { return s.dyn && s.dyn->errors != 0u; }
 
 // ---- put-with-signal over NVLink --------------------------------------------------------
-// Block-level wait: the first two threads spin on the two local flags until the neighbours
-// raised them to step_no; bounded, so a dead or out-of-order neighbour ends in kSlabErrTimeout
-// instead of a hang.  Every thread of the block must call it.
+// One thread spins on a local flag until the neighbour raised it to step_no; bounded, so a dead
+// or out-of-order neighbour ends in kSlabErrTimeout instead of a hang.
+__device__ __forceinline__ void slab_spin(const SlabRef& s, const uint32_t* f) {
+    if (!f || (s.dyn->errors & kSlabErrTimeout)) return;
+    uint32_t v = 0;
+    for (unsigned spins = 0;; spins++) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (v >= s.step_no) break;
+        if (spins > (1u << 26)) {  // ~ 20 s of 300 ns naps
+            atomicOr(&s.dyn->errors, kSlabErrTimeout);
+            break;
+        }
+        __nanosleep(300);
+    }
+    __threadfence_system();
+}
+
+// Block-level wait for both neighbours.  Every thread of the block must call it.
+// (No indexing of s.wait by a thread-dependent value: the kernel parameter would be copied
+// into local memory for it.)
 __device__ __forceinline__ void slab_block_wait(const SlabRef& s) {
     if (!s.wait[0] && !s.wait[1]) return;
-    // (no indexing of s.wait by a thread-dependent value: the kernel parameter would be copied
-    // into local memory for it)
-    const uint32_t* f = threadIdx.x == 0 ? s.wait[0] : s.wait[1];
-    if (threadIdx.x < 2 && f && !(s.dyn->errors & kSlabErrTimeout)) {
-        uint32_t v = 0;
-        for (unsigned spins = 0;; spins++) {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            if (v >= s.step_no) break;
-            if (spins > (1u << 26)) {  // ~ 20 s of 300 ns naps
-                atomicOr(&s.dyn->errors, kSlabErrTimeout);
-                break;
-            }
-            __nanosleep(300);
-        }
-        __threadfence_system();
-    }
+    if (threadIdx.x < 2) slab_spin(s, threadIdx.x == 0 ? s.wait[0] : s.wait[1]);
     __syncthreads();
 }
 
-// Grid-level signal: the block that finishes LAST raises the flags at both neighbours.  Every
-// thread of every block must call it, after its last store into a neighbour's memory.
-__device__ __forceinline__ void slab_grid_signal(const SlabRef& s) {
+// Warp-level wait for the neighbour below and / or above: the gathers call it only for the
+// groups of the first / last owned layer, the only ones that read ghost slots -- every other
+// warp starts at once and works while the halo is still on its way.  Every lane must call it.
+__device__ __forceinline__ void slab_warp_wait(const SlabRef& s, bool below, bool above) {
+    if (!s.wait[0] && !s.wait[1]) return;
+    const int lane = threadIdx.x & 31;
+    if (lane == 0 && below) slab_spin(s, s.wait[0]);
+    if (lane == 1 && above) slab_spin(s, s.wait[1]);
+    __syncwarp();
+}
+
+// Grid-level signal: of the `blocks` blocks that take part, the one that finishes LAST raises
+// the flags at both neighbours.  Every thread of every participating block must call it, after
+// its last store into a neighbour's memory; wrote_remote says whether this thread made one
+// (a block without any skips the system-scope fence).
+__device__ __forceinline__ void slab_grid_signal(const SlabRef& s, bool wrote_remote, uint32_t blocks) {
     if (!s.done) return;
-    __syncthreads();
+    const int any_remote = __syncthreads_or(wrote_remote ? 1 : 0);
     if (threadIdx.x == 0) {
-        __threadfence_system();  // this block's remote stores (ordered by the barrier) first
+        if (any_remote) __threadfence_system();  // this block's remote stores (ordered by the barrier) first
         const uint32_t ticket = atomicAdd(s.done, 1u);
-        if (ticket == gridDim.x * gridDim.y - 1u) {
+        if (ticket == blocks - 1u) {
             __threadfence_system();
             if (s.raise[0])
                 asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(s.raise[0]), "r"(s.step_no) : "memory");

@@ -122,7 +122,7 @@ k_slab_info(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ of
         if (peer_down) peer_down[kLcHeader + i] = cd;
         if (peer_up) peer_up[kLcHeader + i] = cu;
     }
-    slab_grid_signal(slab);
+    slab_grid_signal(slab, peer_down != nullptr || peer_up != nullptr, gridDim.x);
 }
 
 // The two ghost layers of the table, one block each: (waits for the neighbour's layer-count
@@ -291,7 +291,7 @@ k_migrants(const float4* __restrict__ pos, const float4* __restrict__ vel, float
 // neither.
 __global__ void k_slab_sync(SlabRef slab) {
     slab_block_wait(slab);
-    slab_grid_signal(slab);
+    slab_grid_signal(slab, false, 1u);
 }
 
 }  // namespace wc

@@ -144,14 +144,18 @@ k_finish_sort(const uint32_t* __restrict__ offsets, int G, int row_begin, int ro
               ReorderIO io, SlabRef slab, const uint32_t* __restrict__ big_cells,
               const uint32_t* __restrict__ big_count, uint32_t big_cap, int passes) {
     static_assert(kGroupRows == kBigThreads, "one block shape for both parts");
+    bool remote = false;
     if (!slab_dead(slab)) {
         if (groups && row_begin + (int)blockIdx.x * kGroupRows < row_end)
             build_groups_block(offsets, G, row_begin, row_end, groups, num_groups);
-        if (ids)
-            reorder_big_cells(ids, scratch, offsets, base, io, peer_halo_of(slab), big_cells,
-                              big_count, big_cap, passes);
+        if (ids) {
+            const PeerHalo peer = peer_halo_of(slab);
+            remote = (peer.pos[0] || peer.pos[1]) && *big_count > 0u;
+            reorder_big_cells(ids, scratch, offsets, base, io, peer, big_cells, big_count, big_cap,
+                              passes);
+        }
     }
-    slab_grid_signal(slab);
+    slab_grid_signal(slab, remote, gridDim.x);
 }
 
 inline int finish_sort_blocks(int rows) {
@@ -591,7 +595,7 @@ __device__ __forceinline__ GroupCtx group_prologue(const float4* pos_rho, const 
 }
 
 template <bool kDebug>
-__device__ __forceinline__ void density_group(float4* pos_rho, float4* __restrict__ vel_pres,
+__device__ __forceinline__ bool density_group(float4* pos_rho, float4* __restrict__ vel_pres,
                                               const uint32_t* __restrict__ offsets,
                                               const SphConsts& c, const uint4* __restrict__ groups,
                                               const uint32_t* __restrict__ num_groups,
@@ -601,7 +605,10 @@ __device__ __forceinline__ void density_group(float4* pos_rho, float4* __restric
     const int lane = threadIdx.x & 31;
     float4 p;
     const GroupCtx x = group_prologue(pos_rho, c, groups, num_groups, kDensityWarps, &p);
-    if (!x.active) return;
+    if (!x.active) return false;
+    // slab mode: only the groups of the first / last owned layer read the neighbours' halo
+    // positions (stored into this rank's ghost slots by their reorder)
+    slab_warp_wait(slab, x.gg.rz <= 1, x.gg.rz >= c.Gz - 2);
     DensityAcc<kDebug> acc;
     if (list.idx) {
         acc.idx_out = list.idx + (size_t)x.g * list.cap_words * 32 + lane;
@@ -611,10 +618,11 @@ __device__ __forceinline__ void density_group(float4* pos_rho, float4* __restric
     gather_group(pos_rho, vel_pres, offsets, c, stage, acc, x.valid, x.gg, p,
                  make_float4(0, 0, 0, 0));
     if (list.idx && lane == 0) list.words[x.g] = acc.overflow ? kListOverflow : acc.words_used;
-    if (!x.valid) return;
+    if (!x.valid) return false;
     float rho, pres;
     finish_density(c, acc.sum0 + acc.sum1, p.x, p.y, p.z, &rho, &pres);
     const PeerHalo peer = peer_halo_of(slab);
+    bool remote = false;
     // In place like density.comp:135; the gather only reads x,y,z, which do not change.
     reinterpret_cast<float*>(pos_rho)[4 * (size_t)x.i + 3] = rho;
     reinterpret_cast<float*>(vel_pres)[4 * (size_t)x.i + 3] = pres;
@@ -624,21 +632,24 @@ __device__ __forceinline__ void density_group(float4* pos_rho, float4* __restric
     if (peer.pos[0] && t < peer.n_first) {
         reinterpret_cast<float*>(peer.pos[0])[4 * (size_t)(peer.dst[0] + t) + 3] = rho;
         reinterpret_cast<float*>(peer.vel[0])[4 * (size_t)(peer.dst[0] + t) + 3] = pres;
+        remote = true;
     }
     if (peer.pos[1] && t >= peer.hi_begin) {
         reinterpret_cast<float*>(peer.pos[1])[4 * (size_t)(peer.dst[1] + t - peer.hi_begin) + 3] = rho;
         reinterpret_cast<float*>(peer.vel[1])[4 * (size_t)(peer.dst[1] + t - peer.hi_begin) + 3] = pres;
+        remote = true;
     }
     if (kDebug) {  // the self pair was accepted iff the particle's own d2 is 0 (finite position)
         const bool self = dist2(p.x - p.x, p.y - p.y, p.z - p.z) < c.T;
         neighbour_counts[x.t] = acc.nn - (self ? 1u : 0u);
     }
+    return remote;
 }
 
-// density.comp:81-137, one warp per group.  Slab mode with attached neighbours: the block
-// first waits for the neighbours' halo positions (stored into this rank's ghost slots by
-// their reorder), and the block that finishes last tells them that this rank's halo density /
-// pressure is in their ghost copies.
+// density.comp:81-137, one warp per group.  Slab mode: the launch is sized by capacity, so
+// the blocks beyond the group table leave at once; with attached neighbours the warps of the
+// boundary layers wait for the halo positions, and the block that finishes last tells the
+// neighbours that this rank's halo density / pressure is in their ghost copies.
 template <bool kDebug>
 __global__ void __launch_bounds__(kDensityWarps * 32, WC_DENSITY_MIN_BLOCKS)
 k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
@@ -646,11 +657,16 @@ k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
                const uint4* __restrict__ groups, const uint32_t* __restrict__ num_groups,
                uint32_t* __restrict__ neighbour_counts, NbrList list, SlabRef slab) {
     __shared__ DensityStage s_stage[kDensityWarps];
-    slab_block_wait(slab);
+    uint32_t blocks = gridDim.x;
+    if (slab.dyn) {  // at least one block stays to raise the signal, also in a dead step
+        blocks = max(1u, (*num_groups + kDensityWarps - 1u) / kDensityWarps);
+        if (blockIdx.x >= blocks) return;
+    }
+    bool remote = false;
     if (!slab_dead(slab))
-        density_group<kDebug>(pos_rho, vel_pres, offsets, c, groups, num_groups, neighbour_counts,
-                              list, slab, s_stage[threadIdx.x >> 5]);
-    slab_grid_signal(slab);
+        remote = density_group<kDebug>(pos_rho, vel_pres, offsets, c, groups, num_groups,
+                                       neighbour_counts, list, slab, s_stage[threadIdx.x >> 5]);
+    slab_grid_signal(slab, remote, blocks);
 }
 
 // update.comp:134-232.  With a valid neighbour list the warp replays the density pass's
@@ -666,13 +682,14 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
               SlabRef slab) {
     extern __shared__ __align__(16) unsigned char s_dyn[];  // kUpdateWarps stages (may exceed 48 KB)
     UpdateStage* s_stage = reinterpret_cast<UpdateStage*>(s_dyn);
-    // slab mode with attached neighbours: the ghosts' density / pressure must have arrived
-    slab_block_wait(slab);
     if (slab_dead(slab)) return;
     const int lane = threadIdx.x & 31;
     float4 p;
     const GroupCtx x = group_prologue(pos_rho, c, groups, num_groups, kUpdateWarps, &p);
     if (!x.active) return;
+    // slab mode with attached neighbours: the ghosts' density / pressure must have arrived
+    // before a group of the first / last owned layer reads them
+    slab_warp_wait(slab, x.gg.rz <= 1, x.gg.rz >= c.Gz - 2);
     float4 v = make_float4(0, 0, 0, 0);
     if (x.valid) v = vel_pres[x.i];
     UpdateAcc acc;

@@ -211,9 +211,11 @@ def run(args, rank, world, local):
     assert int(n_now.item()) == n_total, (int(n_now.item()), n_total)  # nothing lost in migration
     value = n_total / (ms_per_step * 1e-3)
 
-    # ---- e2e: every rank's slab goes host -> device and back every step, through ONE C-ABI
-    # call per step (wc_slab_step_peer_host: H2D of the pinned input, the step, and the result
-    # stored into the pinned output by the update kernel itself)
+    # ---- e2e: every rank's slab goes host -> device and back every step.  Two routes through
+    # the C-ABI are timed and the faster one is the line's e2e (the other is reported beside it):
+    # wc_slab_step_peer_host (the update kernel stores the result into the pinned output itself:
+    # no extra pass, but the stores cross PCIe at kernel speed) and upload + step + download
+    # (pack kernel + copy engine).
     e2e = None
     if not args.no_e2e:
         cur = b.download(1)
@@ -222,40 +224,50 @@ def run(args, rank, world, local):
         n_cur = cur.shape[0]
         h_in[:n_cur].copy_(torch.from_numpy(cur))
         del cur
-        steps_e = max(3, min(args.steps, 10))
-        h2d = d2h = 0
-        fused = peer and hasattr(b.fluid, "slab_step_peer_host")
-        barrier()
-        ev0 = torch.cuda.Event(enable_timing=True)
-        ev1 = torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        for _ in range(steps_e):
-            if fused:
-                info = b.fluid.slab_step_peer_host((h_in.data_ptr(), n_cur), h_out.data_ptr(), cap,
-                                                   FRAME_DT)
+        steps_e = max(3, min(args.steps, 6))
+
+        def timed_e2e(fused):
+            nonlocal h_in, h_out, n_cur
+            h2d = d2h = 0
+            barrier()
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            for _ in range(steps_e):
                 h2d += n_cur * 32
-                n_cur = info["n_owned"]
-            else:
-                b.fluid.upload((h_in.data_ptr(), n_cur))
-                h2d += n_cur * 32
-                one_step()
-                n_cur = b.num_particles
-                b.fluid.download(1, out=(h_out.data_ptr(), n_cur))
-            d2h += n_cur * 32
-            h_in, h_out = h_out, h_in
-        ev1.record(stream)
-        barrier()
-        ms_e = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
-        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
-        tot = torch.tensor([h2d, d2h], device="cuda", dtype=torch.int64)
-        dist.all_reduce(tot)
-        ms_e_step = float(ms_e.item()) / steps_e
-        e2e = {"value": n_total / (ms_e_step * 1e-3), "unit": bench.UNIT, "ms_per_step": ms_e_step,
-               "h2d_bytes_per_step": int(tot[0].item()) // steps_e,
-               "d2h_bytes_per_step": int(tot[1].item()) // steps_e,
-               "api": "wc_slab_step_peer_host per rank (pinned host AoS in and out; D2H fused into "
-                      "the update kernel)" if fused else
-                      "wc_upload_particles + slab step + wc_download_particles per rank"}
+                if fused:
+                    info = b.fluid.slab_step_peer_host((h_in.data_ptr(), n_cur), h_out.data_ptr(),
+                                                       cap, FRAME_DT)
+                    n_cur = info["n_owned"]
+                else:
+                    b.fluid.upload((h_in.data_ptr(), n_cur))
+                    one_step()
+                    n_cur = b.num_particles
+                    b.fluid.download(1, out=(h_out.data_ptr(), n_cur))
+                d2h += n_cur * 32
+                h_in, h_out = h_out, h_in
+            ev1.record(stream)
+            barrier()
+            ms_e = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+            dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+            tot = torch.tensor([h2d, d2h], device="cuda", dtype=torch.int64)
+            dist.all_reduce(tot)
+            ms_step = float(ms_e.item()) / steps_e
+            return {"value": n_total / (ms_step * 1e-3), "unit": bench.UNIT, "ms_per_step": ms_step,
+                    "h2d_bytes_per_step": int(tot[0].item()) // steps_e,
+                    "d2h_bytes_per_step": int(tot[1].item()) // steps_e,
+                    "api": "wc_slab_step_peer_host per rank (pinned host AoS in and out; D2H fused "
+                           "into the update kernel)" if fused else
+                           "wc_upload_particles + wc_slab_step_peer + wc_download_particles per rank "
+                           "(pinned host AoS; pack kernel + copy engine)"}
+
+        routes = [timed_e2e(False)]
+        if peer:
+            routes.append(timed_e2e(True))
+        routes.sort(key=lambda r: r["ms_per_step"])
+        e2e = routes[0]
+        if len(routes) > 1:
+            e2e["other_route"] = {k: routes[1][k] for k in ("ms_per_step", "api")}
         del h_in, h_out
 
     per_stage = {k: v / n_stage for k, v in stage_ms.items()}
