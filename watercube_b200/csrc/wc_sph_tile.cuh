@@ -57,6 +57,10 @@ constexpr int kDensityWarps = WC_DENSITY_WARPS;  // warps (= groups) per block, 
 #ifndef WC_DROP_SELF
 #define WC_DROP_SELF 1
 #endif
+// 1: the density pass's cull stores without a branch (rejected candidates go to a dump slot).
+#ifndef WC_CULL_BRANCHFREE
+#define WC_CULL_BRANCHFREE 0
+#endif
 // 1: list candidates that no target of the group accepted as padding slots.
 #ifndef WC_LIST_DROP_UNUSED
 #define WC_LIST_DROP_UNUSED 1
@@ -239,10 +243,10 @@ struct alignas(16) DensityStage {
     static constexpr int kBatch = kChunk;
     static constexpr int kDepth = kCullDepth;
     static constexpr int kWrap = kRing - 1;  // ring: batches start at slot 0 or kChunk
-    float x[kRing];
-    float y[kRing];
-    float z[kRing];
-    uint32_t j[kRing];
+    float x[kRing + 32 * WC_CULL_BRANCHFREE];  // (+ one dump slot per lane, see gather_group)
+    float y[kRing + 32 * WC_CULL_BRANCHFREE];
+    float z[kRing + 32 * WC_CULL_BRANCHFREE];
+    uint32_t j[kRing + 32 * WC_CULL_BRANCHFREE];
     __device__ __forceinline__ void put(int slot, float4 q, uint32_t j_, const float4*) {
         x[slot] = q.x, y[slot] = q.y, z[slot] = q.z, j[slot] = j_;
     }
@@ -522,6 +526,17 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
                 const float ex = fmaxf(fmaxf(bx0 - q[k].x, q[k].x - bx1), 0.0f);
                 const float ey = fmaxf(fmaxf(by0 - q[k].y, q[k].y - by1), 0.0f);
                 const float ez = fmaxf(fmaxf(bz0 - q[k].z, q[k].z - bz1), 0.0f);
+#if WC_CULL_BRANCHFREE
+                if constexpr (Stage::kWrap != 0) {
+                    // no branch: a rejected candidate is stored too, into a per-lane dump slot
+                    const bool keep = (j < end) & (ex * ex + ey * ey + ez * ez < Tcull);
+                    const unsigned km = __ballot_sync(full, keep);
+                    const int at = cnt + __popc(km & lt);
+                    st.put(keep ? ((head + at) & Stage::kWrap) : (kRing + lane), q[k], j, vel_pres);
+                    cnt += __popc(km);
+                } else
+#endif
+                {
                 const bool keep = j < end && ex * ex + ey * ey + ez * ez < Tcull;
                 const unsigned km = __ballot_sync(full, keep);
                 if (keep) {
@@ -529,6 +544,7 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
                     st.put(Stage::kWrap ? ((head + at) & Stage::kWrap) : at, q[k], j, vel_pres);
                 }
                 cnt += __popc(km);
+                }
             }
             if (cnt >= Stage::kBatch) {
                 __syncwarp();
