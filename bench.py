@@ -59,6 +59,8 @@ def parse_args():
                     help="N = 1 default workload: skip the 16M roofline case (BASELINE configs[2])")
     ap.add_argument("--no-weak-baseline", action="store_true",
                     help="N > 1: skip rank 0's single-GPU run at the per-GPU load")
+    ap.add_argument("--no-rebalance", action="store_true",
+                    help="N > 1: skip the mid-run refresh of the slab cuts")
     ap.add_argument("--no-slab-parity", action="store_true",
                     help="N > 1: skip the bit-for-bit check against rank 0's whole-grid run")
     ap.add_argument("--no-e2e", action="store_true")

@@ -534,10 +534,10 @@ int preload_slab_kernels() {
     WC_CUDA(cudaFuncGetAttributes(&a, k_scatter_ids));
     WC_CUDA(cudaFuncGetAttributes(&a, k_reorder));
     WC_CUDA(cudaFuncGetAttributes(&a, k_finish_sort));
-    WC_CUDA(cudaFuncGetAttributes(&a, k_density_tile<false>));
-    WC_CUDA(cudaFuncGetAttributes(&a, k_density_tile<true>));
-    WC_CUDA(cudaFuncGetAttributes(&a, k_update_tile<false>));
-    WC_CUDA(cudaFuncGetAttributes(&a, k_update_tile<true>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_density_tile<false, true>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_density_tile<true, true>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_update_tile<false, true>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_update_tile<true, true>));
     WC_CUDA(cudaFuncGetAttributes(&a, k_density_v1<false>));
     WC_CUDA(cudaFuncGetAttributes(&a, k_density_v1<true>));
     WC_CUDA(cudaFuncGetAttributes(&a, k_update_v1<false>));

@@ -57,10 +57,6 @@ constexpr int kDensityWarps = WC_DENSITY_WARPS;  // warps (= groups) per block, 
 #ifndef WC_DROP_SELF
 #define WC_DROP_SELF 1
 #endif
-// 1: the density pass's cull stores without a branch (rejected candidates go to a dump slot).
-#ifndef WC_CULL_BRANCHFREE
-#define WC_CULL_BRANCHFREE 0
-#endif
 // 1: list candidates that no target of the group accepted as padding slots.
 #ifndef WC_LIST_DROP_UNUSED
 #define WC_LIST_DROP_UNUSED 1
@@ -243,10 +239,10 @@ struct alignas(16) DensityStage {
     static constexpr int kBatch = kChunk;
     static constexpr int kDepth = kCullDepth;
     static constexpr int kWrap = kRing - 1;  // ring: batches start at slot 0 or kChunk
-    float x[kRing + 32 * WC_CULL_BRANCHFREE];  // (+ one dump slot per lane, see gather_group)
-    float y[kRing + 32 * WC_CULL_BRANCHFREE];
-    float z[kRing + 32 * WC_CULL_BRANCHFREE];
-    uint32_t j[kRing + 32 * WC_CULL_BRANCHFREE];
+    float x[kRing];
+    float y[kRing];
+    float z[kRing];
+    uint32_t j[kRing];
     __device__ __forceinline__ void put(int slot, float4 q, uint32_t j_, const float4*) {
         x[slot] = q.x, y[slot] = q.y, z[slot] = q.z, j[slot] = j_;
     }
@@ -526,17 +522,6 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
                 const float ex = fmaxf(fmaxf(bx0 - q[k].x, q[k].x - bx1), 0.0f);
                 const float ey = fmaxf(fmaxf(by0 - q[k].y, q[k].y - by1), 0.0f);
                 const float ez = fmaxf(fmaxf(bz0 - q[k].z, q[k].z - bz1), 0.0f);
-#if WC_CULL_BRANCHFREE
-                if constexpr (Stage::kWrap != 0) {
-                    // no branch: a rejected candidate is stored too, into a per-lane dump slot
-                    const bool keep = (j < end) & (ex * ex + ey * ey + ez * ez < Tcull);
-                    const unsigned km = __ballot_sync(full, keep);
-                    const int at = cnt + __popc(km & lt);
-                    st.put(keep ? ((head + at) & Stage::kWrap) : (kRing + lane), q[k], j, vel_pres);
-                    cnt += __popc(km);
-                } else
-#endif
-                {
                 const bool keep = j < end && ex * ex + ey * ey + ez * ez < Tcull;
                 const unsigned km = __ballot_sync(full, keep);
                 if (keep) {
@@ -544,7 +529,6 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
                     st.put(Stage::kWrap ? ((head + at) & Stage::kWrap) : at, q[k], j, vel_pres);
                 }
                 cnt += __popc(km);
-                }
             }
             if (cnt >= Stage::kBatch) {
                 __syncwarp();
@@ -579,13 +563,24 @@ struct GroupCtx {
     GroupGeom gg;
 };
 
+template <bool kSlab>
 __device__ __forceinline__ GroupCtx group_prologue(const float4* pos_rho, const SphConsts& c,
                                                    const uint4* __restrict__ groups,
                                                    const uint32_t* __restrict__ num_groups,
-                                                   int warps_per_block, float4* p_out) {
+                                                   int warps_per_block, float4* p_out,
+                                                   const SlabRef& slab) {
     GroupCtx x;
     const int lane = threadIdx.x & 31;
-    x.g = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    // Slab mode: the blocks start in the middle of the group table and wrap around, so the
+    // groups of the first / last owned layer -- the only ones that wait for a neighbour's halo
+    // -- come up about half-way through the kernel, when the halo has long arrived.
+    unsigned block = blockIdx.x;
+    if constexpr (kSlab) {
+        const unsigned nb = max(1u, (*num_groups + (unsigned)warps_per_block - 1u) / (unsigned)warps_per_block);
+        block = block + nb / 2u;
+        block = block >= nb ? block - nb : block;
+    }
+    x.g = (int)block * warps_per_block + (threadIdx.x >> 5);
     const uint4 rec = groups[x.g];  // the table is allocated for the launch bound; may be stale
     x.active = (uint32_t)x.g < *num_groups;
     x.valid = false;
@@ -610,7 +605,7 @@ __device__ __forceinline__ GroupCtx group_prologue(const float4* pos_rho, const 
     return x;
 }
 
-template <bool kDebug>
+template <bool kDebug, bool kSlab>
 __device__ __forceinline__ bool density_group(float4* pos_rho, float4* __restrict__ vel_pres,
                                               const uint32_t* __restrict__ offsets,
                                               const SphConsts& c, const uint4* __restrict__ groups,
@@ -620,11 +615,11 @@ __device__ __forceinline__ bool density_group(float4* pos_rho, float4* __restric
                                               DensityStage& stage) {
     const int lane = threadIdx.x & 31;
     float4 p;
-    const GroupCtx x = group_prologue(pos_rho, c, groups, num_groups, kDensityWarps, &p);
+    const GroupCtx x = group_prologue<kSlab>(pos_rho, c, groups, num_groups, kDensityWarps, &p, slab);
     if (!x.active) return false;
     // slab mode: only the groups of the first / last owned layer read the neighbours' halo
     // positions (stored into this rank's ghost slots by their reorder)
-    slab_warp_wait(slab, x.gg.rz <= 1, x.gg.rz >= c.Gz - 2);
+    if constexpr (kSlab) slab_warp_wait(slab, x.gg.rz <= 1, x.gg.rz >= c.Gz - 2);
     DensityAcc<kDebug> acc;
     if (list.idx) {
         acc.idx_out = list.idx + (size_t)x.g * list.cap_words * 32 + lane;
@@ -637,23 +632,25 @@ __device__ __forceinline__ bool density_group(float4* pos_rho, float4* __restric
     if (!x.valid) return false;
     float rho, pres;
     finish_density(c, acc.sum0 + acc.sum1, p.x, p.y, p.z, &rho, &pres);
-    const PeerHalo peer = peer_halo_of(slab);
     bool remote = false;
     // In place like density.comp:135; the gather only reads x,y,z, which do not change.
     reinterpret_cast<float*>(pos_rho)[4 * (size_t)x.i + 3] = rho;
     reinterpret_cast<float*>(vel_pres)[4 * (size_t)x.i + 3] = pres;
     // a halo particle: density and pressure also go into the neighbour's ghost copy (whose
     // x,y,z and velocity the reorder already stored there)
-    const uint32_t t = (uint32_t)x.t;
-    if (peer.pos[0] && t < peer.n_first) {
-        reinterpret_cast<float*>(peer.pos[0])[4 * (size_t)(peer.dst[0] + t) + 3] = rho;
-        reinterpret_cast<float*>(peer.vel[0])[4 * (size_t)(peer.dst[0] + t) + 3] = pres;
-        remote = true;
-    }
-    if (peer.pos[1] && t >= peer.hi_begin) {
-        reinterpret_cast<float*>(peer.pos[1])[4 * (size_t)(peer.dst[1] + t - peer.hi_begin) + 3] = rho;
-        reinterpret_cast<float*>(peer.vel[1])[4 * (size_t)(peer.dst[1] + t - peer.hi_begin) + 3] = pres;
-        remote = true;
+    if constexpr (kSlab) {
+        const PeerHalo peer = peer_halo_of(slab);
+        const uint32_t t = (uint32_t)x.t;
+        if (peer.pos[0] && t < peer.n_first) {
+            reinterpret_cast<float*>(peer.pos[0])[4 * (size_t)(peer.dst[0] + t) + 3] = rho;
+            reinterpret_cast<float*>(peer.vel[0])[4 * (size_t)(peer.dst[0] + t) + 3] = pres;
+            remote = true;
+        }
+        if (peer.pos[1] && t >= peer.hi_begin) {
+            reinterpret_cast<float*>(peer.pos[1])[4 * (size_t)(peer.dst[1] + t - peer.hi_begin) + 3] = rho;
+            reinterpret_cast<float*>(peer.vel[1])[4 * (size_t)(peer.dst[1] + t - peer.hi_begin) + 3] = pres;
+            remote = true;
+        }
     }
     if (kDebug) {  // the self pair was accepted iff the particle's own d2 is 0 (finite position)
         const bool self = dist2(p.x - p.x, p.y - p.y, p.z - p.z) < c.T;
@@ -666,29 +663,33 @@ __device__ __forceinline__ bool density_group(float4* pos_rho, float4* __restric
 // the blocks beyond the group table leave at once; with attached neighbours the warps of the
 // boundary layers wait for the halo positions, and the block that finishes last tells the
 // neighbours that this rank's halo density / pressure is in their ghost copies.
-template <bool kDebug>
+template <bool kDebug, bool kSlab>
 __global__ void __launch_bounds__(kDensityWarps * 32, WC_DENSITY_MIN_BLOCKS)
 k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
                const uint32_t* __restrict__ offsets, SphConsts c,
                const uint4* __restrict__ groups, const uint32_t* __restrict__ num_groups,
                uint32_t* __restrict__ neighbour_counts, NbrList list, SlabRef slab) {
     __shared__ DensityStage s_stage[kDensityWarps];
-    uint32_t blocks = gridDim.x;
-    if (slab.dyn) {  // at least one block stays to raise the signal, also in a dead step
-        blocks = max(1u, (*num_groups + kDensityWarps - 1u) / kDensityWarps);
+    if constexpr (!kSlab) {  // whole grid: no slab code at all in this instantiation
+        density_group<kDebug, false>(pos_rho, vel_pres, offsets, c, groups, num_groups,
+                                     neighbour_counts, list, slab, s_stage[threadIdx.x >> 5]);
+    } else {
+        // at least one block stays to raise the signal, also in a dead step
+        const uint32_t blocks = max(1u, (*num_groups + kDensityWarps - 1u) / kDensityWarps);
         if (blockIdx.x >= blocks) return;
+        bool remote = false;
+        if (!slab_dead(slab))
+            remote = density_group<kDebug, true>(pos_rho, vel_pres, offsets, c, groups, num_groups,
+                                                 neighbour_counts, list, slab,
+                                                 s_stage[threadIdx.x >> 5]);
+        slab_grid_signal(slab, remote, blocks);
     }
-    bool remote = false;
-    if (!slab_dead(slab))
-        remote = density_group<kDebug>(pos_rho, vel_pres, offsets, c, groups, num_groups,
-                                       neighbour_counts, list, slab, s_stage[threadIdx.x >> 5]);
-    slab_grid_signal(slab, remote, blocks);
 }
 
 // update.comp:134-232.  With a valid neighbour list the warp replays the density pass's
 // words; without one (list.idx == nullptr, or this group overflowed its list) it runs the
 // cull + distance test itself.
-template <bool kDebug>
+template <bool kDebug, bool kSlab>
 __global__ void __launch_bounds__(kUpdateWarps * 32, WC_UPDATE_MIN_BLOCKS)
 k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel_pres,
               const uint32_t* __restrict__ offsets, SphConsts c,
@@ -698,14 +699,17 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
               SlabRef slab) {
     extern __shared__ __align__(16) unsigned char s_dyn[];  // kUpdateWarps stages (may exceed 48 KB)
     UpdateStage* s_stage = reinterpret_cast<UpdateStage*>(s_dyn);
-    if (slab_dead(slab)) return;
+    if constexpr (kSlab) {
+        if (slab_dead(slab)) return;
+        if (blockIdx.x >= max(1u, (*num_groups + kUpdateWarps - 1u) / kUpdateWarps)) return;
+    }
     const int lane = threadIdx.x & 31;
     float4 p;
-    const GroupCtx x = group_prologue(pos_rho, c, groups, num_groups, kUpdateWarps, &p);
+    const GroupCtx x = group_prologue<kSlab>(pos_rho, c, groups, num_groups, kUpdateWarps, &p, slab);
     if (!x.active) return;
     // slab mode with attached neighbours: the ghosts' density / pressure must have arrived
     // before a group of the first / last owned layer reads them
-    slab_warp_wait(slab, x.gg.rz <= 1, x.gg.rz >= c.Gz - 2);
+    if constexpr (kSlab) slab_warp_wait(slab, x.gg.rz <= 1, x.gg.rz >= c.Gz - 2);
     float4 v = make_float4(0, 0, 0, 0);
     if (x.valid) v = vel_pres[x.i];
     UpdateAcc acc;
@@ -781,17 +785,51 @@ struct GroupTable {
 
 inline int blocks_for(int groups, int warps) { return (groups + warps - 1) / warps; }
 
+template <bool kSlab>
+inline void launch_density_tile_t(float4* pos_rho, float4* vel_pres, const uint32_t* offsets,
+                                  const SphConsts& c, const GroupTable& gt,
+                                  uint32_t* neighbour_counts, NbrList list, cudaStream_t stream,
+                                  const SlabRef& slab) {
+    const int blocks = blocks_for(gt.max_groups, kDensityWarps);
+    if (neighbour_counts)
+        k_density_tile<true, kSlab><<<blocks, kDensityWarps * 32, 0, stream>>>(
+            pos_rho, vel_pres, offsets, c, gt.groups, gt.count, neighbour_counts, list, slab);
+    else
+        k_density_tile<false, kSlab><<<blocks, kDensityWarps * 32, 0, stream>>>(
+            pos_rho, vel_pres, offsets, c, gt.groups, gt.count, nullptr, list, slab);
+}
+
 inline void launch_density_tile(float4* pos_rho, float4* vel_pres, const uint32_t* offsets,
                                 const SphConsts& c, const GroupTable& gt,
                                 uint32_t* neighbour_counts, NbrList list, cudaStream_t stream,
-                                const SlabRef& peer = SlabRef{}) {
-    const int blocks = blocks_for(gt.max_groups, kDensityWarps);
-    if (neighbour_counts)
-        k_density_tile<true><<<blocks, kDensityWarps * 32, 0, stream>>>(
-            pos_rho, vel_pres, offsets, c, gt.groups, gt.count, neighbour_counts, list, peer);
+                                const SlabRef& slab = SlabRef{}) {
+    if (slab.dyn)
+        launch_density_tile_t<true>(pos_rho, vel_pres, offsets, c, gt, neighbour_counts, list, stream, slab);
     else
-        k_density_tile<false><<<blocks, kDensityWarps * 32, 0, stream>>>(
-            pos_rho, vel_pres, offsets, c, gt.groups, gt.count, nullptr, list, peer);
+        launch_density_tile_t<false>(pos_rho, vel_pres, offsets, c, gt, neighbour_counts, list, stream, slab);
+}
+
+template <bool kSlab>
+inline void launch_update_tile_t(const float4* pos_rho, const float4* vel_pres,
+                                 const uint32_t* offsets, const SphConsts& c, const GroupTable& gt,
+                                 float4* pos_out, float4* vel_out, float4* forces, NbrList list,
+                                 cudaStream_t stream, float4* aos_out, const SlabRef& slab) {
+    const int blocks = blocks_for(gt.max_groups, kUpdateWarps);
+    constexpr size_t smem = kUpdateWarps * sizeof(UpdateStage);
+    if (smem > 48 * 1024) {  // opt-in size; the attribute is per device, so set it per launch
+        if (forces)
+            cudaFuncSetAttribute(k_update_tile<true, kSlab>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        else
+            cudaFuncSetAttribute(k_update_tile<false, kSlab>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    if (forces)
+        k_update_tile<true, kSlab><<<blocks, kUpdateWarps * 32, smem, stream>>>(
+            pos_rho, vel_pres, offsets, c, gt.groups, gt.count, pos_out, vel_out, forces,
+            list, aos_out, slab);
+    else
+        k_update_tile<false, kSlab><<<blocks, kUpdateWarps * 32, smem, stream>>>(
+            pos_rho, vel_pres, offsets, c, gt.groups, gt.count, pos_out, vel_out, nullptr,
+            list, aos_out, slab);
 }
 
 inline void launch_update_tile(const float4* pos_rho, const float4* vel_pres,
@@ -799,22 +837,10 @@ inline void launch_update_tile(const float4* pos_rho, const float4* vel_pres,
                                float4* pos_out, float4* vel_out, float4* forces, NbrList list,
                                cudaStream_t stream, float4* aos_out = nullptr,
                                const SlabRef& slab = SlabRef{}) {
-    const int blocks = blocks_for(gt.max_groups, kUpdateWarps);
-    constexpr size_t smem = kUpdateWarps * sizeof(UpdateStage);
-    if (smem > 48 * 1024) {  // opt-in size; the attribute is per device, so set it per launch
-        if (forces)
-            cudaFuncSetAttribute(k_update_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        else
-            cudaFuncSetAttribute(k_update_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
-    if (forces)
-        k_update_tile<true><<<blocks, kUpdateWarps * 32, smem, stream>>>(
-            pos_rho, vel_pres, offsets, c, gt.groups, gt.count, pos_out, vel_out, forces,
-            list, aos_out, slab);
+    if (slab.dyn)
+        launch_update_tile_t<true>(pos_rho, vel_pres, offsets, c, gt, pos_out, vel_out, forces, list, stream, aos_out, slab);
     else
-        k_update_tile<false><<<blocks, kUpdateWarps * 32, smem, stream>>>(
-            pos_rho, vel_pres, offsets, c, gt.groups, gt.count, pos_out, vel_out, nullptr,
-            list, aos_out, slab);
+        launch_update_tile_t<false>(pos_rho, vel_pres, offsets, c, gt, pos_out, vel_out, forces, list, stream, aos_out, slab);
 }
 
 }  // namespace wc
