@@ -592,6 +592,34 @@ def test_uniform_box_sweep_1m_subcase(capi, oracle, nb):
     assert np.isfinite(out).all()
 
 
+@pytest.mark.parametrize("nb", [30, 200])
+def test_uniform_box_sweep_8m_full_size(capi, oracle, nb):
+    """BASELINE.json configs[4] at its FULL size (uniform random box, 8M particles, box 3.5) at
+    both ends of the smoothing-length sweep: sort outputs and neighbour counts bit-exact over all
+    8M particles, density / pressure within the fp32 tolerances."""
+    n = 8_000_000
+    h = scenes.smoothing_length_for_neighbours(float(nb))
+    sc = scenes.uniform_box(n, size=3.5, h=h, seed=300 + nb)
+    p = oracle_params(oracle, sc)
+    d = oracle.derive(p)
+    s = oracle.sort(sc.particles, d.bin_size, p.grid_res)
+    P, nc = oracle.density(s["sorted"], s["counts"], s["offsets"], p, nthreads=oracle.host_threads())
+    P = oracle.as_f32(P)
+    assert 0.8 * nb < nc.mean() < 1.1 * nb
+    with gpu_fluid(capi, sc, capi.FLAG_DEBUG_OUTPUTS) as fl:
+        fl.upload(sc.particles)
+        fl.sort_only()
+        fl.density_only()
+        got = fl.cells(neighbour_counts=True)
+        srt = fl.download(2)
+    for key in ("cell_ids", "counts", "offsets", "perm"):
+        np.testing.assert_array_equal(got[key], s[key], err_msg=key)
+    np.testing.assert_array_equal(got["neighbour_counts"], nc)
+    wall = wall_term_magnitude(srt, sc.size, h)
+    assert np.all(np.abs(srt[:, 3] - P[:, 3]) <= RTOL_RHO * (np.abs(P[:, 3]) + wall))
+    assert np.all(np.abs(srt[:, 7] - P[:, 7]) <= RTOL_P * (np.abs(P[:, 7]) + 100.0))
+
+
 def test_neighbour_list_replay_equals_full_search(capi):
     """The update pass replays the density pass's neighbour list; with the list disabled,
     or too small (per-warp overflow -> that warp searches again), results are bit-identical."""

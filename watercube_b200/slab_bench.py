@@ -204,8 +204,11 @@ def run(args, rank, world, local):
     launches = b.fluid.launch_count() - launches0
     clocks = sampler.stop(t_wall0, t_wall1)
     # stage split from a few extra steps (reading the stage events syncs, so not in the timed loop)
+    # (every rank starts such a step together: the waits for a neighbour's message sit inside the
+    # kernels now, so a stage time includes them -- this keeps them to the real dependencies)
     n_stage = max(1, min(3, args.steps))
     for _ in range(n_stage):
+        barrier()
         one_step()
         for k, v in b.fluid.stage_times().items():
             stage_ms[k] += v
