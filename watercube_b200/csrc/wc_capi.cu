@@ -235,7 +235,9 @@ SlabRef slab_ref(const wc_handle* h, int wait_phase = -1, int raise_phase = -1, 
     r.Cg = (uint32_t)h->Cg;
     r.cap = (uint32_t)h->cap;
     r.step_no = value >= 0 ? (uint32_t)value : h->step_no;
-    if (done_slot >= 0) r.done = h->done + done_slot;
+    // (the block counter only matters when somebody is signalled -- or to close the step)
+    if (done_slot >= 0 && (h->peer_mode() || raise_phase < 0 || done_slot == kDoneMigrants))
+        r.done = h->done + done_slot;
     for (int d = 0; d < 2; d++) {
         if (!h->peer[d].on) continue;
         r.peer_pos[d] = h->peer[d].pos1;
@@ -393,6 +395,11 @@ int sort_reorder_phase(wc_handle* h, bool timed, int n_in, int n_sorted) {
         k_scatter_ids<<<div_up(n_in, 256), 256, 0, h->stream>>>(
             h->cell_ids, h->ranks, h->offsets, n_in, h->ids, (uint32_t)h->Cg, slab_ref(h), h->M);
         WC_CHECK_LAUNCH(h);
+    }
+    // slab mode: the ghost layers of the table -- which wait for the neighbours' layer counts --
+    // go here, behind the ID scatter (it only needs the owned layers), so that wait is covered
+    if (h->slab && (rc = slab_ghost_phase(h))) return rc;
+    if (moved) {
         k_reorder<<<div_up(n_sorted, 256), 256, 0, h->stream>>>(
             h->ids, h->offsets, n_sorted, bin, G, h->zbase, (uint32_t)h->Cg, io, slab_ref(h),
             h->big_cells, h->big_count, (uint32_t)h->big_cap);
@@ -1245,11 +1252,9 @@ int wc_slab_sync_info(wc_handle* h, int32_t info[8]) {
 int wc_slab_reorder(wc_handle* h) {
     WC_NEED_SLAB(h);
     if (h->step_no == 0) return fail(WC_ERR_INVALID, "wc_slab_reorder needs wc_slab_sort_count");
-    int rc;
-    // ghost layers: the neighbours' counts, scanned so the halo slices sit right before /
-    // after the owned slice: [Cg - n_glow, Cg) and [Cg + n, Cg + n + n_ghigh)
-    if ((rc = slab_ghost_phase(h))) return rc;
-    // launch bounds by capacity: the virtual input [M | owned | M] and the owned region
+    // launch bounds by capacity: the virtual input [M | owned | M] and the owned region.  (The
+    // ghost layers -- the neighbours' counts, scanned so the halo slices sit right before / after
+    // the owned slice: [Cg - n_glow, Cg) and [Cg + n, Cg + n + n_ghigh) -- are queued inside.)
     return sort_reorder_phase(h, true, h->M + h->cap + h->M, h->cap);
 }
 

@@ -133,19 +133,37 @@ __device__ __forceinline__ void slab_block_wait(const SlabRef& s) {
 
 // Warp-level wait for the neighbour below and / or above: the gathers call it only for the
 // groups of the first / last owned layer, the only ones that read ghost slots -- every other
-// warp starts at once and works while the halo is still on its way.  Every lane must call it.
+// warp starts at once and works while the halo is still on its way.  Every lane must call it
+// with the same arguments.  The arguments pass through a vote, all lanes poll together and the
+// loop ends on a vote: ptxas can then see that the control flow is warp-uniform.  With one
+// polling lane (or a condition it cannot prove uniform) it loses its proof that the warp is
+// converged for the REST of the kernel and wraps every ballot / shuffle of the gather loop in a
+// convergence check (+6 % instructions in k_density_tile, profiles/r02_variant_sweep.md).
 __device__ __forceinline__ void slab_warp_wait(const SlabRef& s, bool below, bool above) {
-    if (!s.wait[0] && !s.wait[1]) return;
-    const int lane = threadIdx.x & 31;
-    if (lane == 0 && below) slab_spin(s, s.wait[0]);
-    if (lane == 1 && above) slab_spin(s, s.wait[1]);
-    __syncwarp();
+    const uint32_t* f0 = __any_sync(0xffffffffu, below) ? s.wait[0] : nullptr;
+    const uint32_t* f1 = __any_sync(0xffffffffu, above) ? s.wait[1] : nullptr;
+    if (!f0 && !f1) return;
+    for (unsigned spins = 0;; spins++) {
+        uint32_t v0 = s.step_no, v1 = s.step_no;
+        if (f0) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v0) : "l"(f0) : "memory");
+        if (f1) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v1) : "l"(f1) : "memory");
+        const bool timed_out = spins > (1u << 26) || (s.dyn->errors & kSlabErrTimeout);
+        if (__all_sync(0xffffffffu, (v0 >= s.step_no && v1 >= s.step_no) || timed_out)) {
+            if (timed_out && (threadIdx.x & 31) == 0) atomicOr(&s.dyn->errors, kSlabErrTimeout);
+            break;
+        }
+        __nanosleep(300);
+    }
+    __threadfence_system();
 }
 
 // Grid-level signal: of the `blocks` blocks that take part, the one that finishes LAST raises
 // the flags at both neighbours.  Every thread of every participating block must call it, after
 // its last store into a neighbour's memory; wrote_remote says whether this thread made one
-// (a block without any skips the system-scope fence).
+// (a block without any skips the system-scope fence).  (No spin loop in here: a kernel that
+// holds one under a lane-dependent condition loses ptxas' proof that its warps are converged,
+// and every ballot / shuffle of the gather loop is then wrapped in a convergence check --
+// +6 % instructions in k_density_tile, profiles/r02_variant_sweep.md.)
 __device__ __forceinline__ void slab_grid_signal(const SlabRef& s, bool wrote_remote, uint32_t blocks) {
     if (!s.done) return;
     const int any_remote = __syncthreads_or(wrote_remote ? 1 : 0);

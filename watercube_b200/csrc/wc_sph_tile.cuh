@@ -57,6 +57,10 @@ constexpr int kDensityWarps = WC_DENSITY_WARPS;  // warps (= groups) per block, 
 #ifndef WC_DROP_SELF
 #define WC_DROP_SELF 1
 #endif
+// 1: slab mode, the gathers start in the middle of the group table (see group_prologue).
+#ifndef WC_SLAB_MIDDLE_OUT
+#define WC_SLAB_MIDDLE_OUT 1
+#endif
 // 1: list candidates that no target of the group accepted as padding slots.
 #ifndef WC_LIST_DROP_UNUSED
 #define WC_LIST_DROP_UNUSED 1
@@ -568,21 +572,25 @@ __device__ __forceinline__ GroupCtx group_prologue(const float4* pos_rho, const 
                                                    const uint4* __restrict__ groups,
                                                    const uint32_t* __restrict__ num_groups,
                                                    int warps_per_block, float4* p_out,
-                                                   const SlabRef& slab) {
+                                                   unsigned vblock, unsigned needed_blocks) {
     GroupCtx x;
     const int lane = threadIdx.x & 31;
-    // Slab mode: the blocks start in the middle of the group table and wrap around, so the
-    // groups of the first / last owned layer -- the only ones that wait for a neighbour's halo
-    // -- come up about half-way through the kernel, when the halo has long arrived.
-    unsigned block = blockIdx.x;
-    if constexpr (kSlab) {
-        const unsigned nb = max(1u, (*num_groups + (unsigned)warps_per_block - 1u) / (unsigned)warps_per_block);
-        block = block + nb / 2u;
-        block = block >= nb ? block - nb : block;
+    // Slab mode: the (virtual) blocks start in the middle of the group table and wrap around,
+    // so the groups of the first / last owned layer -- the only ones that wait for a
+    // neighbour's halo -- come up about half-way through the kernel, when the halo has long
+    // arrived.
+    unsigned block = vblock;
+    if constexpr (kSlab && WC_SLAB_MIDDLE_OUT) {
+        block = block + needed_blocks / 2u;
+        block = block >= needed_blocks ? block - needed_blocks : block;
     }
     x.g = (int)block * warps_per_block + (threadIdx.x >> 5);
     const uint4 rec = groups[x.g];  // the table is allocated for the launch bound; may be stale
     x.active = (uint32_t)x.g < *num_groups;
+    // (slab mode: an idle warp of the last block does not exit, it goes on to the block's
+    // signal; the vote lets ptxas see that the branch around the gather is warp-uniform, see
+    // slab_warp_wait); a block beyond the table must not wrap around into it
+    if constexpr (kSlab) x.active = __any_sync(0xffffffffu, x.active && vblock < needed_blocks);
     x.valid = false;
     x.t = x.i = 0;
     *p_out = make_float4(0, 0, 0, 0);
@@ -612,10 +620,12 @@ __device__ __forceinline__ bool density_group(float4* pos_rho, float4* __restric
                                               const uint32_t* __restrict__ num_groups,
                                               uint32_t* __restrict__ neighbour_counts,
                                               const NbrList& list, const SlabRef& slab,
-                                              DensityStage& stage) {
+                                              DensityStage& stage, unsigned vblock,
+                                              unsigned needed_blocks) {
     const int lane = threadIdx.x & 31;
     float4 p;
-    const GroupCtx x = group_prologue<kSlab>(pos_rho, c, groups, num_groups, kDensityWarps, &p, slab);
+    const GroupCtx x = group_prologue<kSlab>(pos_rho, c, groups, num_groups, kDensityWarps, &p,
+                                             vblock, needed_blocks);
     if (!x.active) return false;
     // slab mode: only the groups of the first / last owned layer read the neighbours' halo
     // positions (stored into this rank's ghost slots by their reorder)
@@ -661,8 +671,8 @@ __device__ __forceinline__ bool density_group(float4* pos_rho, float4* __restric
 
 // density.comp:81-137, one warp per group.  Slab mode: the launch is sized by capacity, so
 // the blocks beyond the group table leave at once; with attached neighbours the warps of the
-// boundary layers wait for the halo positions, and the block that finishes last tells the
-// neighbours that this rank's halo density / pressure is in their ghost copies.
+// boundary layers wait for the halo positions, and once every block is done the neighbours
+// are told that this rank's halo density / pressure is in their ghost copies.
 template <bool kDebug, bool kSlab>
 __global__ void __launch_bounds__(kDensityWarps * 32, WC_DENSITY_MIN_BLOCKS)
 k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
@@ -672,7 +682,8 @@ k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
     __shared__ DensityStage s_stage[kDensityWarps];
     if constexpr (!kSlab) {  // whole grid: no slab code at all in this instantiation
         density_group<kDebug, false>(pos_rho, vel_pres, offsets, c, groups, num_groups,
-                                     neighbour_counts, list, slab, s_stage[threadIdx.x >> 5]);
+                                     neighbour_counts, list, slab, s_stage[threadIdx.x >> 5],
+                                     blockIdx.x, gridDim.x);
     } else {
         // at least one block stays to raise the signal, also in a dead step
         const uint32_t blocks = max(1u, (*num_groups + kDensityWarps - 1u) / kDensityWarps);
@@ -681,7 +692,7 @@ k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
         if (!slab_dead(slab))
             remote = density_group<kDebug, true>(pos_rho, vel_pres, offsets, c, groups, num_groups,
                                                  neighbour_counts, list, slab,
-                                                 s_stage[threadIdx.x >> 5]);
+                                                 s_stage[threadIdx.x >> 5], blockIdx.x, blocks);
         slab_grid_signal(slab, remote, blocks);
     }
 }
@@ -690,22 +701,21 @@ k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
 // words; without one (list.idx == nullptr, or this group overflowed its list) it runs the
 // cull + distance test itself.
 template <bool kDebug, bool kSlab>
-__global__ void __launch_bounds__(kUpdateWarps * 32, WC_UPDATE_MIN_BLOCKS)
-k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel_pres,
-              const uint32_t* __restrict__ offsets, SphConsts c,
-              const uint4* __restrict__ groups, const uint32_t* __restrict__ num_groups,
-              float4* __restrict__ pos_out, float4* __restrict__ vel_out,
-              float4* __restrict__ forces, NbrList list, float4* __restrict__ aos_out,
-              SlabRef slab) {
-    extern __shared__ __align__(16) unsigned char s_dyn[];  // kUpdateWarps stages (may exceed 48 KB)
-    UpdateStage* s_stage = reinterpret_cast<UpdateStage*>(s_dyn);
-    if constexpr (kSlab) {
-        if (slab_dead(slab)) return;
-        if (blockIdx.x >= max(1u, (*num_groups + kUpdateWarps - 1u) / kUpdateWarps)) return;
-    }
+__device__ __forceinline__ void update_group(const float4* __restrict__ pos_rho,
+                                             const float4* __restrict__ vel_pres,
+                                             const uint32_t* __restrict__ offsets,
+                                             const SphConsts& c, const uint4* __restrict__ groups,
+                                             const uint32_t* __restrict__ num_groups,
+                                             float4* __restrict__ pos_out,
+                                             float4* __restrict__ vel_out,
+                                             float4* __restrict__ forces, const NbrList& list,
+                                             float4* __restrict__ aos_out, const SlabRef& slab,
+                                             UpdateStage& st, unsigned vblock,
+                                             unsigned needed_blocks) {
     const int lane = threadIdx.x & 31;
     float4 p;
-    const GroupCtx x = group_prologue<kSlab>(pos_rho, c, groups, num_groups, kUpdateWarps, &p, slab);
+    const GroupCtx x = group_prologue<kSlab>(pos_rho, c, groups, num_groups, kUpdateWarps, &p,
+                                             vblock, needed_blocks);
     if (!x.active) return;
     // slab mode with attached neighbours: the ghosts' density / pressure must have arrived
     // before a group of the first / last owned layer reads them
@@ -713,7 +723,6 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
     float4 v = make_float4(0, 0, 0, 0);
     if (x.valid) v = vel_pres[x.i];
     UpdateAcc acc;
-    UpdateStage& st = s_stage[threadIdx.x >> 5];
     uint32_t nw = kListOverflow;
     if (list.idx) nw = list.words[x.g];
     if (nw == kListOverflow) {
@@ -774,6 +783,32 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
     if (aos_out) {
         __stcs(&aos_out[2 * (size_t)x.t], po);
         __stcs(&aos_out[2 * (size_t)x.t + 1], vo);
+    }
+}
+
+// (slab mode: launch sizing as in k_density_tile)
+template <bool kDebug, bool kSlab>
+__global__ void __launch_bounds__(kUpdateWarps * 32, WC_UPDATE_MIN_BLOCKS)
+k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel_pres,
+              const uint32_t* __restrict__ offsets, SphConsts c,
+              const uint4* __restrict__ groups, const uint32_t* __restrict__ num_groups,
+              float4* __restrict__ pos_out, float4* __restrict__ vel_out,
+              float4* __restrict__ forces, NbrList list, float4* __restrict__ aos_out,
+              SlabRef slab) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];  // kUpdateWarps stages (may exceed 48 KB)
+    UpdateStage* s_stage = reinterpret_cast<UpdateStage*>(s_dyn);
+    UpdateStage& st = s_stage[threadIdx.x >> 5];
+    if constexpr (!kSlab) {
+        update_group<kDebug, false>(pos_rho, vel_pres, offsets, c, groups, num_groups, pos_out,
+                                    vel_out, forces, list, aos_out, slab, st, blockIdx.x, gridDim.x);
+    } else {
+        // A dead step (sticky error in the slab record) has an empty group table: the arena
+        // memset zeroed the count and k_finish_sort did not build one.  (No early exit of the
+        // blocks beyond the table and no test of the error word up here: with either one ptxas
+        // allocates the walk loop 8 % longer; update_group's own test of the count covers both.)
+        const uint32_t blocks = max(1u, (*num_groups + kUpdateWarps - 1u) / kUpdateWarps);
+        update_group<kDebug, true>(pos_rho, vel_pres, offsets, c, groups, num_groups, pos_out,
+                                   vel_out, forces, list, aos_out, slab, st, blockIdx.x, blocks);
     }
 }
 
