@@ -58,6 +58,9 @@ constexpr int kDensityWarps = WC_DENSITY_WARPS;  // warps (= groups) per block, 
 #define WC_DROP_SELF 1
 #endif
 // 1: slab mode, the gathers start in the middle of the group table (see group_prologue).
+#ifndef WC_UNIFORM_NW
+#define WC_UNIFORM_NW 1
+#endif
 #ifndef WC_SLAB_MIDDLE_OUT
 #define WC_SLAB_MIDDLE_OUT 1
 #endif
@@ -725,6 +728,9 @@ __device__ __forceinline__ void update_group(const float4* __restrict__ pos_rho,
     UpdateAcc acc;
     uint32_t nw = kListOverflow;
     if (list.idx) nw = list.words[x.g];
+#if WC_UNIFORM_NW
+    nw = __shfl_sync(0xffffffffu, nw, 0);  // the same word in every lane; this way ptxas knows it too
+#endif
     if (nw == kListOverflow) {
         gather_group(pos_rho, vel_pres, offsets, c, st, acc, x.valid, x.gg, p, v);
     } else {
