@@ -99,6 +99,37 @@ typedef struct wc_step_params {
     float mouse_dir[3];          /* "mouseRayDirection" uniform */
 } wc_step_params;
 
+/* Physics the reference's report lists as future work (report.pdf section 6, "Future Work":
+ * wall particles after Harada et al., surface tension after Yan et al.).
+ * There is no reference code for it: oracle/wc_oracle.h defines the arithmetic, the CUDA path
+ * is checked against that.  A handle starts with flags == 0, which is the reference's step bit
+ * for bit (its own kernel instantiations, untouched by any of this); wc_set_physics switches
+ * the handle to the instantiations that know the flags.
+ *
+ * WC_PHYS_WALL_PARTICLES replaces the pseudo wall density of density.comp:57-79 and the wall
+ * force of update.comp:71-100 (quirks Q2-Q6): the wall particles' density contribution is a
+ * function of the distance s to the wall only (Harada's "wall weight function", here the
+ * closed-form integral of wall_rest_density * W_poly6 over the half space behind the wall),
+ * and a particle closer than wall_distance is pushed back with the acceleration
+ * wall_stiffness * (wall_distance - s) / dt^2 along the wall normal.  The box clamp of
+ * update.comp:202-227 stays as the last resort.
+ *
+ * WC_PHYS_SURFACE_TENSION adds the colour-field force of Mueller et al. 2003 (the model Yan et
+ * al. build on): n_i = sum_j m/rho_j grad W_poly6(r_ij), lap_i = sum_j m/rho_j lap W_poly6(r_ij)
+ * over the particle itself and its neighbours with 0 < |r_ij| < h (summed like the density:
+ * self term included), and F_i += -surface_tension * lap_i * n_i / |n_i| where
+ * |n_i| > surface_threshold. */
+#define WC_PHYS_WALL_PARTICLES 1u
+#define WC_PHYS_SURFACE_TENSION 2u
+typedef struct wc_physics {
+    uint32_t flags;          /* WC_PHYS_*; 0 = the reference's physics */
+    float surface_tension;   /* default 50 */
+    float surface_threshold; /* default 7 */
+    float wall_stiffness;    /* default 0.5: half of the penetration undone per step */
+    float wall_distance;     /* default 0.01 (the reference's particle radius) */
+    float wall_rest_density; /* mass x number density of the wall particles; <= 0: rest_density */
+} wc_physics;
+
 /* Constants derived in Fluid::setup (src/core/Fluid.cpp:206-216). */
 typedef struct wc_derived {
     int32_t num_bins;
@@ -144,6 +175,11 @@ int wc_device_count(int32_t* count);
  * two particle buffers, count/offset/sorted buffers and scratch on p->device. */
 typedef struct wc_handle wc_handle;
 int wc_create(const wc_params* p, wc_handle** out);
+/* Extended physics (see wc_physics): defaults with flags = 0; set / read back per handle.  Takes
+ * effect from the next step on; WC_ERR_INVALID for unknown flag bits or non-finite values. */
+int wc_default_physics(wc_physics* ph);
+int wc_set_physics(wc_handle* h, const wc_physics* ph);
+int wc_get_physics(const wc_handle* h, wc_physics* ph);
 int wc_destroy(wc_handle* h);
 int wc_get_derived(const wc_handle* h, wc_derived* d);
 

@@ -36,7 +36,18 @@ class Params(C.Structure):
         ("time_scale", C.c_float),
         ("mouse_origin", C.c_float * 3),
         ("mouse_dir", C.c_float * 3),
+        # extended physics (wc_oracle.h WCO_PHYS_*); 0 = the reference's step
+        ("physics_flags", C.c_uint32),
+        ("surface_tension", C.c_float),
+        ("surface_threshold", C.c_float),
+        ("wall_stiffness", C.c_float),
+        ("wall_distance", C.c_float),
+        ("wall_rest_density", C.c_float),
     ]
+
+
+PHYS_WALL_PARTICLES = 1
+PHYS_SURFACE_TENSION = 2
 
 
 class Derived(C.Structure):

@@ -61,6 +61,10 @@ struct Consts {
     T mo[3], md[3];
     T eps;  // the literal 1e-16 of update.comp:131,181,198 as a float
     int G;
+    // extended physics (wc_oracle.h: WCO_PHYS_*); phys == 0 is the reference's step
+    uint32_t phys;
+    T sigma, n_min, wall_k, wall_d, wall_rho;
+    T wallC;  // pi/4 * poly6C * h^9: the half-space integral of W_poly6 is wallC * 128/315
 };
 
 template <typename T>
@@ -86,6 +90,16 @@ Consts<T> make_consts(const wco_params* p) {
     }
     c.eps = (T)1e-16f;
     c.G = p->grid_res;
+    c.phys = p->physics_flags;
+    c.sigma = (T)p->surface_tension;
+    c.n_min = (T)p->surface_threshold;
+    c.wall_k = (T)p->wall_stiffness;
+    c.wall_d = (T)p->wall_distance;
+    c.wall_rho = p->wall_rest_density > 0.0f ? (T)p->wall_rest_density : (T)p->rest_density;
+    {   // one fp32 constant for both precisions (the CUDA host derives the very same float)
+        const double h = (double)d.kernel_radius;
+        c.wallC = (T)(float)(0.78539816339744830962 * (double)d.poly6_const * std::pow(h, 9.0));
+    }
     return c;
 }
 
@@ -154,6 +168,47 @@ inline void wall_forces(const Consts<T>& c, const T* p, T* force) {
         }
     }
     for (int b = 0; b < 3; b++) force[b] = force[b] * (T)0.01f;
+}
+
+// --- extended physics (not in the reference; wc_oracle.h WCO_PHYS_WALL_PARTICLES) ----------
+// Wall weight function: wall_rho * integral of W_poly6 over the half space at distance >= s,
+//   wall_rho * wallC * (128/315 - P(u)),  u = s / h,  P(u) = u - 4u^3/3 + 6u^5/5 - 4u^7/7 + u^9/9
+// (Horner in u^2, this operation order), summed over the walls closer than h.
+template <typename T>
+inline T wall_weight(const Consts<T>& c, T s) {
+    const T u = s / c.h, u2 = u * u;
+    T P = (T)(1.0f / 9.0f);
+    P = P * u2 + (T)(-4.0f / 7.0f);
+    P = P * u2 + (T)(6.0f / 5.0f);
+    P = P * u2 + (T)(-4.0f / 3.0f);
+    P = P * u2 + (T)1;
+    P = P * u;
+    return (c.wall_rho * c.wallC) * ((T)(128.0f / 315.0f) - P);
+}
+template <typename T>
+inline T wall_density_particles(const Consts<T>& c, const T* p) {
+    T density = 0;
+    for (int a = 0; a < 3; a++) {
+        if (p[a] < c.h) {
+            density += wall_weight(c, p[a]);
+        } else if (p[a] > c.size - c.h) {
+            density += wall_weight(c, c.size - p[a]);
+        }
+    }
+    return density;
+}
+// Penetration push: acceleration wall_k * (wall_d - s) / dt^2 along the inward normal.
+template <typename T>
+inline void wall_push(const Consts<T>& c, const T* p, T dt, T* acc) {
+    const T scale = c.wall_k / (dt * dt);
+    for (int a = 0; a < 3; a++) {
+        acc[a] = 0;
+        if (p[a] < c.wall_d) {
+            acc[a] = (c.wall_d - p[a]) * scale;
+        } else if (p[a] > c.size - c.wall_d) {
+            acc[a] = -((c.wall_d - (c.size - p[a])) * scale);
+        }
+    }
 }
 
 // GLSL min/max: min(x,y) = y < x ? y : x, max(x,y) = x < y ? y : x.
@@ -251,7 +306,10 @@ inline void density_one(const wco_particle* P, int i, const uint32_t* counts,
                            nn++;
                        });
     T pos[3] = {(T)P[i].position[0], (T)P[i].position[1], (T)P[i].position[2]};
-    *rho_out = density + wall_density(c, pos);  // density.comp:126 (Q4: stored WITH wall term)
+    if (c.phys & WCO_PHYS_WALL_PARTICLES)
+        *rho_out = density + wall_density_particles(c, pos);
+    else
+        *rho_out = density + wall_density(c, pos);  // density.comp:126 (Q4: stored WITH wall term)
     const T q = density / c.rho0;               // density.comp:133 (Q4: pressure WITHOUT it)
     *pres_out = c.P0 + c.k * (((q * q) * q) - (T)1);
     if (ncount) *ncount = nn;
@@ -272,6 +330,7 @@ inline void update_one(const wco_particle* P, int i, const uint32_t* counts,
     // test aid, not reference math: per component, the sum of the MAGNITUDES of everything
     // that is added into F -- the scale rounding errors of the sum are proportional to
     T S[3] = {std::abs(ext[0]), std::abs(ext[1]), std::abs(ext[2])};
+    T cfN[3] = {0, 0, 0}, cfNabs[3] = {0, 0, 0}, cfL = 0, cfLabs = 0;
 
     for_each_neighbour(
         P, i, counts, offsets, bin_f, h_f, c.G,
@@ -304,15 +363,59 @@ inline void update_one(const wco_particle* P, int i, const uint32_t* counts,
                 for (int a = 0; a < 3; a++)
                     S[a] += c.mu * std::abs((c.m * ((std::abs((T)P[j].velocity[a]) +
                                                      std::abs(vel_i[a])) / rho_j)) * wv);
+            // colour field of the surface tension (extended physics): the sums are kept
+            // without the common factor -6 * poly6C (grad W_poly6 = -6 C t^2 r,
+            // lap W_poly6 = -6 C t (3 h^2 - 7 r^2), t = h^2 - r^2)
+            if (c.phys & WCO_PHYS_SURFACE_TENSION) {
+                const T d2 = sizeof(T) == sizeof(float) ? (T)dist2_f32(rx, ry, rz) : d * d;
+                if (d2 > (T)0) {
+                    const T t = c.h * c.h - d2;
+                    const T a = c.m / rho_j;
+                    for (int k = 0; k < 3; k++) {
+                        cfN[k] += (a * (t * t)) * r[k];
+                        cfNabs[k] += std::abs((a * (t * t)) * r[k]);
+                    }
+                    const T l = (a * t) * ((T)3 * (c.h * c.h) - (T)7 * d2);
+                    cfL += l;
+                    cfLabs += std::abs(l);
+                }
+            }
         });
 
     // update.comp:191
     T mf[3] = {0, 0, 0}, wf[3];
     if (mouse_hits) mouse_force(c, pos, pres_i, mf);
-    wall_forces(c, pos, wf);
+    if (c.phys & WCO_PHYS_WALL_PARTICLES) {
+        // as a force density, so that the acceleration F / (rho_i + eps) below is the push
+        wall_push(c, pos, dt, wf);
+        for (int a = 0; a < 3; a++) wf[a] = wf[a] * (rho_i + c.eps);
+    } else {
+        wall_forces(c, pos, wf);
+    }
+    T st[3] = {0, 0, 0}, st_scale[3] = {0, 0, 0};
+    if (c.phys & WCO_PHYS_SURFACE_TENSION) {
+        {   // the particle's own term of the colour field's Laplacian (its gradient term is zero)
+            const T l = (c.m / rho_i) * ((c.h * c.h) * ((T)3 * (c.h * c.h)));
+            cfL += l;
+            cfLabs += std::abs(l);
+        }
+        const T gc = (T)-6 * c.poly6C;
+        const T n[3] = {gc * cfN[0], gc * cfN[1], gc * cfN[2]};
+        const T lap = gc * cfL;
+        const T len = std::sqrt((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
+        if (len > c.n_min) {
+            const T f = (-c.sigma * lap) / len;
+            for (int a = 0; a < 3; a++) {
+                st[a] = f * n[a];
+                // first-order error scale of f * n[a] (test aid): errors of lap and of n
+                st_scale[a] = std::abs(c.sigma * gc) *
+                              (cfLabs * std::abs(n[a]) / len + std::abs(lap / gc) * cfNabs[a] / len * (T)2);
+            }
+        }
+    }
     for (int a = 0; a < 3; a++) {
-        ext[a] += mf[a] + wf[a];
-        S[a] += std::abs(mf[a]) + std::abs(wf[a]);
+        ext[a] += (mf[a] + wf[a]) + st[a];
+        S[a] += std::abs(mf[a]) + std::abs(wf[a]) + std::abs(st[a]) + st_scale[a];
         if (term_scale_out) term_scale_out[a] = S[a];
     }
 
@@ -388,6 +491,13 @@ void wco_default_params(wco_params* p) {
     p->mouse_origin[0] = p->mouse_origin[1] = p->mouse_origin[2] = -10.0f;
     p->mouse_dir[0] = -1.0f;
     p->mouse_dir[1] = p->mouse_dir[2] = 0.0f;
+    // extended physics: off; the values used when a flag is set (wc_default_physics has the same)
+    p->physics_flags = 0;
+    p->surface_tension = 50.0f;
+    p->surface_threshold = 7.0f;
+    p->wall_stiffness = 0.5f;
+    p->wall_distance = 0.01f;
+    p->wall_rest_density = 0.0f;
 }
 
 // Fluid::setup, src/core/Fluid.cpp:206-216.  The kernel constants are evaluated in

@@ -225,3 +225,43 @@ def test_checkpoint_carries_the_step_parameters(exe, tmp_path):
     assert res.returncode == 0, res.stderr
     assert json.loads(res.stdout.strip().splitlines()[-1])["total_steps"] == 16
     assert np.array_equal(np.fromfile(second, np.float32), np.fromfile(straight, np.float32))
+
+
+# ---------------------------------------------------------------- extended physics (wc_physics)
+@pytest.mark.gpu
+def test_headless_extended_physics_equals_binding_decomposed_and_restored(exe, tmp_path):
+    """`--wall-particles --surface-tension S` = Fluid::wallParticles / surfaceTension: the same
+    bits as the ctypes binding with wc_set_physics, the same again from two z-slabs, and a
+    checkpoint carries the physics record (restored run continues without the flags repeated)."""
+    from watercube_b200 import capi
+
+    steps = 16
+    phys = ["--wall-particles", "--wall-density", "9000", "--surface-tension", "40"]
+    straight, slabs, ck, resumed = (tmp_path / n for n in ("s.bin", "m.bin", "a.wcb", "r.bin"))
+    res = subprocess.run([exe, "--steps", str(steps), *phys, "--dump", str(straight)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    got = np.fromfile(straight, np.float32).reshape(-1, 8)
+    sc = scenes.dam_break(80000, seed=0)
+    with capi.Fluid(num_particles=sc.n, grid_res=sc.grid_res, size=sc.size) as fl:
+        fl.set_physics(capi.PHYS_WALL_PARTICLES | capi.PHYS_SURFACE_TENSION, surface_tension=40.0,
+                       wall_rest_density=9000.0)
+        fl.upload(sc.particles)
+        for _ in range(steps):
+            fl.step(1.0 / 60.0)
+        ref = fl.download(1)
+        plain = capi.Fluid(num_particles=sc.n, grid_res=sc.grid_res, size=sc.size)
+        plain.upload(sc.particles)
+        for _ in range(steps):
+            plain.step(1.0 / 60.0)
+        assert not np.array_equal(plain.download(1), ref)      # the flags do change the run
+        plain.close()
+    assert np.array_equal(got, ref)
+    subprocess.run([exe, "--steps", str(steps), *phys, "--gpus", "2", "--dump", str(slabs)],
+                   check=True, capture_output=True)
+    assert np.array_equal(np.fromfile(slabs, np.float32).reshape(-1, 8), ref)
+    subprocess.run([exe, "--steps", str(steps // 2), *phys, "--checkpoint", str(ck)], check=True,
+                   capture_output=True)
+    subprocess.run([exe, "--restore", str(ck), "--steps", str(steps // 2), "--dump", str(resumed)],
+                   check=True, capture_output=True)
+    assert np.array_equal(np.fromfile(resumed, np.float32).reshape(-1, 8), ref)

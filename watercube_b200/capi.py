@@ -34,6 +34,7 @@ EXPORTS = (
     "wc_slab_sort_count", "wc_slab_sync_info", "wc_slab_reorder", "wc_slab_density",
     "wc_slab_update", "wc_advect_only", "wc_slab_ipc_export", "wc_slab_peer_open",
     "wc_slab_peer_attach", "wc_diagnose", "wc_slab_step_peer", "wc_slab_step_peer_host",
+    "wc_default_physics", "wc_set_physics", "wc_get_physics",
 )
 
 
@@ -53,6 +54,19 @@ class StepParams(C.Structure):
         ("viscosity_coefficient", C.c_float), ("stiffness", C.c_float),
         ("rest_density", C.c_float), ("rest_pressure", C.c_float),
         ("gravity", C.c_float * 3), ("mouse_origin", C.c_float * 3), ("mouse_dir", C.c_float * 3),
+    ]
+
+
+PHYS_WALL_PARTICLES = 1
+PHYS_SURFACE_TENSION = 2
+
+
+class Physics(C.Structure):
+    """wc_physics: the report's future-work physics (flags 0 = the reference's step)."""
+    _fields_ = [
+        ("flags", C.c_uint32), ("surface_tension", C.c_float), ("surface_threshold", C.c_float),
+        ("wall_stiffness", C.c_float), ("wall_distance", C.c_float),
+        ("wall_rest_density", C.c_float),
     ]
 
 
@@ -165,6 +179,9 @@ def lib():
             "wc_slab_step_peer": [vp, f32, C.POINTER(StepParams), C.POINTER(C.c_int32 * 8)],
             "wc_slab_step_peer_host": [vp, f32, C.POINTER(StepParams), vp, i32, vp, i32,
                                        C.POINTER(C.c_int32 * 8)],
+            "wc_default_physics": [C.POINTER(Physics)],
+            "wc_set_physics": [vp, C.POINTER(Physics)],
+            "wc_get_physics": [vp, C.POINTER(Physics)],
         }
         for name, argtypes in sig.items():
             fn = getattr(L, name)
@@ -238,6 +255,23 @@ class Fluid:
         check(lib().wc_create(C.byref(self.params), C.byref(self._h)))
         self.derived = Derived()
         check(lib().wc_get_derived(self._h, C.byref(self.derived)))
+
+    # -- extended physics (wc_physics; not reference behaviour)
+    def set_physics(self, flags, **values) -> Physics:
+        """Defaults + overrides (surface_tension, surface_threshold, wall_stiffness,
+        wall_distance, wall_rest_density); takes effect from the next step on."""
+        ph = Physics()
+        check(lib().wc_default_physics(C.byref(ph)))
+        ph.flags = int(flags)
+        for k, v in values.items():
+            setattr(ph, k, v)
+        check(lib().wc_set_physics(self._h, C.byref(ph)))
+        return ph
+
+    def physics(self) -> Physics:
+        ph = Physics()
+        check(lib().wc_get_physics(self._h, C.byref(ph)))
+        return ph
 
     # -- lifetime
     def close(self):

@@ -103,6 +103,7 @@ struct wc_handle {
     uint32_t* offsets = nullptr;          // num_bins + 1
     uint32_t* neighbour_counts = nullptr;
     float4* forces = nullptr;
+    wc_physics phys = {};                 // extended physics (flags 0 = the reference's step)
     // density -> update neighbour list (wc_sph_tile.cuh NbrList)
     uint32_t* nbr_idx = nullptr;
     uint32_t* nbr_mask = nullptr;
@@ -185,8 +186,8 @@ namespace {
 
 using namespace wc;
 
-SphConsts make_consts(const wc_handle* h, const wc_step_params& sp, float frame_dt) {
-    SphConsts c;
+SphConstsExt make_consts(const wc_handle* h, const wc_step_params& sp, float frame_dt) {
+    SphConstsExt c;
     c.n = h->n;
     c.first = h->Cg;
     c.G = h->p.grid_res;
@@ -212,6 +213,17 @@ SphConsts make_consts(const wc_handle* h, const wc_step_params& sp, float frame_
     }
     c.dt = frame_dt * h->p.time_scale;  // Fluid.cpp:308
     c.mouse_hits = mouse_ray_hits_box(sp, h->p.size) ? 1 : 0;
+    // extended physics (oracle make_consts derives the same floats)
+    const wc_physics& ph = h->phys;
+    c.phys = ph.flags;
+    c.sigma = ph.surface_tension;
+    c.n_min = ph.surface_threshold;
+    c.grad_m = (-6.0f * c.poly6C) * c.m;
+    c.h2x3 = 3.0f * c.h2;
+    c.wall_acc = ph.wall_stiffness / (c.dt * c.dt);
+    c.wall_d = ph.wall_distance;
+    const float wallC = (float)(0.78539816339744830962 * (double)c.poly6C * std::pow((double)c.h, 9.0));
+    c.wall_w = (ph.wall_rest_density > 0.0f ? ph.wall_rest_density : sp.rest_density) * wallC;
     return c;
 }
 
@@ -439,7 +451,7 @@ int run_sort(wc_handle* h, bool timed) {
 
 int run_density(wc_handle* h, const wc_step_params& sp) {
     if (!h->slab && h->n == 0) return WC_OK;
-    const SphConsts c = make_consts(h, sp, 0.0f);
+    const SphConstsExt c = make_consts(h, sp, 0.0f);
     const bool dbg = h->p.flags & WC_FLAG_DEBUG_OUTPUTS;
     const NbrList list{h->nbr_idx, h->nbr_mask, h->nbr_words, h->nbr_cap_words};
     const bool simple = h->p.flags & WC_FLAG_SIMPLE_KERNELS;
@@ -463,7 +475,7 @@ int run_density(wc_handle* h, const wc_step_params& sp) {
 int run_update(wc_handle* h, const wc_step_params& sp, float frame_dt,
                float4* aos_out = nullptr) {
     if (!h->slab && h->n == 0) return WC_OK;
-    const SphConsts c = make_consts(h, sp, frame_dt);
+    const SphConstsExt c = make_consts(h, sp, frame_dt);
     const bool dbg = h->p.flags & WC_FLAG_DEBUG_OUTPUTS;
     // The list is only trusted when the density pass that built it saw these positions.
     const NbrList list = h->nbr_valid
@@ -541,10 +553,14 @@ int preload_slab_kernels() {
     WC_CUDA(cudaFuncGetAttributes(&a, k_scatter_ids));
     WC_CUDA(cudaFuncGetAttributes(&a, k_reorder));
     WC_CUDA(cudaFuncGetAttributes(&a, k_finish_sort));
-    WC_CUDA(cudaFuncGetAttributes(&a, k_density_tile<false, true>));
-    WC_CUDA(cudaFuncGetAttributes(&a, k_density_tile<true, true>));
-    WC_CUDA(cudaFuncGetAttributes(&a, k_update_tile<false, true>));
-    WC_CUDA(cudaFuncGetAttributes(&a, k_update_tile<true, true>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_density_tile<false, true, false>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_density_tile<true, true, false>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_update_tile<false, true, false>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_update_tile<true, true, false>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_density_tile<false, true, true>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_density_tile<true, true, true>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_update_tile<false, true, true>));
+    WC_CUDA(cudaFuncGetAttributes(&a, k_update_tile<true, true, true>));
     WC_CUDA(cudaFuncGetAttributes(&a, k_density_v1<false>));
     WC_CUDA(cudaFuncGetAttributes(&a, k_density_v1<true>));
     WC_CUDA(cudaFuncGetAttributes(&a, k_update_v1<false>));
@@ -630,6 +646,37 @@ int wc_default_step_params(wc_step_params* sp) {
     return WC_OK;
 }
 
+int wc_default_physics(wc_physics* ph) {
+    if (!ph) return fail(WC_ERR_INVALID, "physics is NULL");
+    ph->flags = 0;
+    ph->surface_tension = 50.0f;
+    ph->surface_threshold = 7.0f;
+    ph->wall_stiffness = 0.5f;
+    ph->wall_distance = 0.01f;
+    ph->wall_rest_density = 0.0f;
+    return WC_OK;
+}
+
+int wc_set_physics(wc_handle* h, const wc_physics* ph) {
+    if (!h || !ph) return fail(WC_ERR_INVALID, "NULL argument");
+    if (ph->flags & ~(WC_PHYS_WALL_PARTICLES | WC_PHYS_SURFACE_TENSION))
+        return fail(WC_ERR_INVALID, "unknown physics flag bits 0x%x", ph->flags);
+    const float v[5] = {ph->surface_tension, ph->surface_threshold, ph->wall_stiffness,
+                        ph->wall_distance, ph->wall_rest_density};
+    for (float x : v)
+        if (!std::isfinite(x)) return fail(WC_ERR_INVALID, "physics values must be finite");
+    if (ph->surface_threshold < 0.0f || ph->wall_stiffness < 0.0f || ph->wall_distance < 0.0f)
+        return fail(WC_ERR_INVALID, "surface_threshold, wall_stiffness and wall_distance must be >= 0");
+    h->phys = *ph;
+    return WC_OK;
+}
+
+int wc_get_physics(const wc_handle* h, wc_physics* ph) {
+    if (!h || !ph) return fail(WC_ERR_INVALID, "NULL argument");
+    *ph = h->phys;
+    return WC_OK;
+}
+
 int wc_derive(const wc_params* p, wc_derived* d) {
     if (!p || !d) return fail(WC_ERR_INVALID, "NULL argument");
     if (p->grid_res < 1 || p->grid_res > 1290)  // G^3 must fit in int32
@@ -701,6 +748,7 @@ int wc_create(const wc_params* p, wc_handle** out) {
     if (!h) return fail(WC_ERR_INVALID, "out of host memory");
     h->p = *p;
     h->d = d;
+    wc_default_physics(&h->phys);
     h->n = p->num_particles;
     h->cap = cap;
     h->slab = slab;

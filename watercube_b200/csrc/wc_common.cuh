@@ -30,6 +30,27 @@ struct SphConsts {
     int mouse_hits;  // update.comp:118-121 evaluated on the host (all-uniform expression)
 };
 
+// Extended physics (include/wc_sph.h: wc_physics, WC_PHYS_*).  Its own parameter type, taken only
+// by the kernel instantiations that know the flags: the reference step's kernels keep their
+// parameter layout (and with it their code, to the instruction).
+struct SphConstsExt : SphConsts {
+    uint32_t phys;   // WC_PHYS_* (never 0 in a launch of an extended instantiation ... or all off)
+    float sigma;     // surface tension coefficient
+    float n_min;     // colour-field gradient length above which a particle is "surface"
+    float grad_m;    // -6 * poly6C * m: common factor of the colour-field sums
+    float h2x3;      // 3 * h * h
+    float wall_acc;  // wall_stiffness / dt^2
+    float wall_d;    // wall_distance
+    float wall_w;    // wall_rest_density * pi/4 * poly6C * h^9 (scale of the wall weight function)
+};
+template <bool kExt>
+struct ConstsOfT { typedef SphConsts type; };
+template <>
+struct ConstsOfT<true> { typedef SphConstsExt type; };
+template <bool kExt>
+using ConstsOf = typename ConstsOfT<kExt>::type;
+constexpr uint32_t kPhysWall = 1u, kPhysTension = 2u;
+
 // ---------------------------------------------------------------------------------------
 // z-slab mode (wc_slab.cuh).  Everything a step learns about itself -- how many particles the
 // slab owns after this step's sort, how many sit in its first / last layer, how many ghosts

@@ -369,15 +369,18 @@ struct DensityAcc {
     }
 };
 
-// Update accumulator.
+// Update accumulator.  kExt: also the colour-field sums of the surface tension (extended
+// physics; their own instantiation, so the reference step's walk loop carries none of it).
+template <bool kExt>
 struct UpdateAcc {
+    ColourField cf;
     // Fp is accumulated without its factor -0.5 * m * spikyC, Fv without m * viscC.
     float Fpx = 0, Fpy = 0, Fpz = 0, Fvx = 0, Fvy = 0, Fvz = 0;
     uint32_t words_used = 0;  // words of the candidate sequence processed so far (no-list path)
 
     // One accepted pair of update.comp:174-187.  A lane without a pick passes stale operands
     // with 1/rho_j forced to zero, which makes the pair a no-op (`on` is informative only).
-    __device__ __forceinline__ void pair(const SphConsts& c, float4 p, float4 v, float4 qa,
+    __device__ __forceinline__ void pair(const ConstsOf<kExt>& c, float4 p, float4 v, float4 qa,
                                          float4 qb, bool on) {
         // x and y of the separation and of the velocity difference as packed pairs: the operands
         // already sit in aligned register pairs (LDS.128 / LDG.128 results)
@@ -395,6 +398,7 @@ struct UpdateAcc {
         Fpx = fmaf(w, rx, Fpx), Fpy = fmaf(w, ry, Fpy), Fpz = fmaf(w, rz, Fpz);
         const float wv = hd * qa.w;                            // update.comp:186-187
         Fvx = fmaf(wv, dvx, Fvx), Fvy = fmaf(wv, dvy, Fvy), Fvz = fmaf(wv, qb.z - v.z, Fvz);
+        if constexpr (kExt) cf.add(c, rx, ry, rz, d2, qa.w);  // (1/rho_j = 0 without a pick)
     }
 
     // Every lane walks its own accepted bits of the staged mask words [0, nwb) -- one flat
@@ -404,7 +408,7 @@ struct UpdateAcc {
     // instructions and its shared-memory load is off the critical path; a pick that finds
     // no bit (empty word, or lane finished) loads nothing and adds zero.
     // Mask rows [nwb, kReplayWords] must be zero.
-    __device__ __forceinline__ void walk(const UpdateStage& st, int nwb, const SphConsts& c,
+    __device__ __forceinline__ void walk(const UpdateStage& st, int nwb, const ConstsOf<kExt>& c,
                                          float4 p, float4 v) {
         const int lane = threadIdx.x & 31;
         // the mask words are addressed through ONE 32-bit shared-memory address (a generic pointer
@@ -452,7 +456,8 @@ struct UpdateAcc {
 
     // No-list path: phase 1 = distance test only -> one bit per staged candidate, then walk.
     __device__ __forceinline__ void process(UpdateStage& st, int /*head = 0*/, int count,
-                                            const SphConsts& c, float4 p, float4 v, float Teff) {
+                                            const ConstsOf<kExt>& c, float4 p, float4 v,
+                                            float Teff) {
         const int lane = threadIdx.x & 31;
         const int nw = count >> 5;
         for (int w = 0; w < nw; w++) {
@@ -479,10 +484,10 @@ struct GroupGeom {
     int ry, rz;        // the group's cell row (rz relative to the table's layer 0)
 };
 
-template <typename Stage, typename Acc>
+template <typename Stage, typename Acc, typename Consts>
 __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4* vel_pres,
                                              const uint32_t* __restrict__ offsets,
-                                             const SphConsts& c, Stage& st, Acc& acc, bool valid,
+                                             const Consts& c, Stage& st, Acc& acc, bool valid,
                                              const GroupGeom& gg, float4 p,
                                              float4 v) {
     const unsigned full = 0xffffffffu;
@@ -616,10 +621,11 @@ __device__ __forceinline__ GroupCtx group_prologue(const float4* pos_rho, const 
     return x;
 }
 
-template <bool kDebug, bool kSlab>
+template <bool kDebug, bool kSlab, bool kExt>
 __device__ __forceinline__ bool density_group(float4* pos_rho, float4* __restrict__ vel_pres,
                                               const uint32_t* __restrict__ offsets,
-                                              const SphConsts& c, const uint4* __restrict__ groups,
+                                              const ConstsOf<kExt>& c,
+                                              const uint4* __restrict__ groups,
                                               const uint32_t* __restrict__ num_groups,
                                               uint32_t* __restrict__ neighbour_counts,
                                               const NbrList& list, const SlabRef& slab,
@@ -644,7 +650,7 @@ __device__ __forceinline__ bool density_group(float4* pos_rho, float4* __restric
     if (list.idx && lane == 0) list.words[x.g] = acc.overflow ? kListOverflow : acc.words_used;
     if (!x.valid) return false;
     float rho, pres;
-    finish_density(c, acc.sum0 + acc.sum1, p.x, p.y, p.z, &rho, &pres);
+    finish_density<kExt>(c, acc.sum0 + acc.sum1, p.x, p.y, p.z, &rho, &pres);
     bool remote = false;
     // In place like density.comp:135; the gather only reads x,y,z, which do not change.
     reinterpret_cast<float*>(pos_rho)[4 * (size_t)x.i + 3] = rho;
@@ -676,15 +682,15 @@ __device__ __forceinline__ bool density_group(float4* pos_rho, float4* __restric
 // the blocks beyond the group table leave at once; with attached neighbours the warps of the
 // boundary layers wait for the halo positions, and once every block is done the neighbours
 // are told that this rank's halo density / pressure is in their ghost copies.
-template <bool kDebug, bool kSlab>
+template <bool kDebug, bool kSlab, bool kExt>
 __global__ void __launch_bounds__(kDensityWarps * 32, WC_DENSITY_MIN_BLOCKS)
 k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
-               const uint32_t* __restrict__ offsets, SphConsts c,
+               const uint32_t* __restrict__ offsets, ConstsOf<kExt> c,
                const uint4* __restrict__ groups, const uint32_t* __restrict__ num_groups,
                uint32_t* __restrict__ neighbour_counts, NbrList list, SlabRef slab) {
     __shared__ DensityStage s_stage[kDensityWarps];
     if constexpr (!kSlab) {  // whole grid: no slab code at all in this instantiation
-        density_group<kDebug, false>(pos_rho, vel_pres, offsets, c, groups, num_groups,
+        density_group<kDebug, false, kExt>(pos_rho, vel_pres, offsets, c, groups, num_groups,
                                      neighbour_counts, list, slab, s_stage[threadIdx.x >> 5],
                                      blockIdx.x, gridDim.x);
     } else {
@@ -693,7 +699,7 @@ k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
         if (blockIdx.x >= blocks) return;
         bool remote = false;
         if (!slab_dead(slab))
-            remote = density_group<kDebug, true>(pos_rho, vel_pres, offsets, c, groups, num_groups,
+            remote = density_group<kDebug, true, kExt>(pos_rho, vel_pres, offsets, c, groups, num_groups,
                                                  neighbour_counts, list, slab,
                                                  s_stage[threadIdx.x >> 5], blockIdx.x, blocks);
         slab_grid_signal(slab, remote, blocks);
@@ -703,11 +709,12 @@ k_density_tile(float4* pos_rho, float4* __restrict__ vel_pres,
 // update.comp:134-232.  With a valid neighbour list the warp replays the density pass's
 // words; without one (list.idx == nullptr, or this group overflowed its list) it runs the
 // cull + distance test itself.
-template <bool kDebug, bool kSlab>
+template <bool kDebug, bool kSlab, bool kExt>
 __device__ __forceinline__ void update_group(const float4* __restrict__ pos_rho,
                                              const float4* __restrict__ vel_pres,
                                              const uint32_t* __restrict__ offsets,
-                                             const SphConsts& c, const uint4* __restrict__ groups,
+                                             const ConstsOf<kExt>& c,
+                                             const uint4* __restrict__ groups,
                                              const uint32_t* __restrict__ num_groups,
                                              float4* __restrict__ pos_out,
                                              float4* __restrict__ vel_out,
@@ -725,7 +732,7 @@ __device__ __forceinline__ void update_group(const float4* __restrict__ pos_rho,
     if constexpr (kSlab) slab_warp_wait(slab, x.gg.rz <= 1, x.gg.rz >= c.Gz - 2);
     float4 v = make_float4(0, 0, 0, 0);
     if (x.valid) v = vel_pres[x.i];
-    UpdateAcc acc;
+    UpdateAcc<kExt> acc;
     uint32_t nw = kListOverflow;
     if (list.idx) nw = list.words[x.g];
 #if WC_UNIFORM_NW
@@ -777,8 +784,8 @@ __device__ __forceinline__ void update_group(const float4* __restrict__ pos_rho,
     if (!x.valid) return;
     const float kp = -0.5f * (c.m * c.spikyC), kv = c.m * c.viscC;
     float4 po, vo, fo;
-    integrate(c, p, v, acc.Fpx * kp, acc.Fpy * kp, acc.Fpz * kp, acc.Fvx * kv, acc.Fvy * kv,
-              acc.Fvz * kv, &po, &vo, kDebug ? &fo : nullptr);
+    integrate<kExt>(c, p, v, acc.Fpx * kp, acc.Fpy * kp, acc.Fpz * kp, acc.Fvx * kv, acc.Fvy * kv,
+                    acc.Fvz * kv, &po, &vo, kDebug ? &fo : nullptr, acc.cf);
     pos_out[x.t] = po;
     vel_out[x.t] = vo;
     if (kDebug) forces[x.t] = fo;
@@ -793,10 +800,10 @@ __device__ __forceinline__ void update_group(const float4* __restrict__ pos_rho,
 }
 
 // (slab mode: launch sizing as in k_density_tile)
-template <bool kDebug, bool kSlab>
+template <bool kDebug, bool kSlab, bool kExt>
 __global__ void __launch_bounds__(kUpdateWarps * 32, WC_UPDATE_MIN_BLOCKS)
 k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel_pres,
-              const uint32_t* __restrict__ offsets, SphConsts c,
+              const uint32_t* __restrict__ offsets, ConstsOf<kExt> c,
               const uint4* __restrict__ groups, const uint32_t* __restrict__ num_groups,
               float4* __restrict__ pos_out, float4* __restrict__ vel_out,
               float4* __restrict__ forces, NbrList list, float4* __restrict__ aos_out,
@@ -805,7 +812,7 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
     UpdateStage* s_stage = reinterpret_cast<UpdateStage*>(s_dyn);
     UpdateStage& st = s_stage[threadIdx.x >> 5];
     if constexpr (!kSlab) {
-        update_group<kDebug, false>(pos_rho, vel_pres, offsets, c, groups, num_groups, pos_out,
+        update_group<kDebug, false, kExt>(pos_rho, vel_pres, offsets, c, groups, num_groups, pos_out,
                                     vel_out, forces, list, aos_out, slab, st, blockIdx.x, gridDim.x);
     } else {
         // A dead step (sticky error in the slab record) has an empty group table: the arena
@@ -813,7 +820,7 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
         // blocks beyond the table and no test of the error word up here: with either one ptxas
         // allocates the walk loop 8 % longer; update_group's own test of the count covers both.)
         const uint32_t blocks = max(1u, (*num_groups + kUpdateWarps - 1u) / kUpdateWarps);
-        update_group<kDebug, true>(pos_rho, vel_pres, offsets, c, groups, num_groups, pos_out,
+        update_group<kDebug, true, kExt>(pos_rho, vel_pres, offsets, c, groups, num_groups, pos_out,
                                    vel_out, forces, list, aos_out, slab, st, blockIdx.x, blocks);
     }
 }
@@ -826,62 +833,73 @@ struct GroupTable {
 
 inline int blocks_for(int groups, int warps) { return (groups + warps - 1) / warps; }
 
-template <bool kSlab>
+// Launchers: the instantiation is chosen from (debug outputs?, slab mode?, extended physics?).
+template <bool kSlab, bool kExt>
 inline void launch_density_tile_t(float4* pos_rho, float4* vel_pres, const uint32_t* offsets,
-                                  const SphConsts& c, const GroupTable& gt,
+                                  const SphConstsExt& c, const GroupTable& gt,
                                   uint32_t* neighbour_counts, NbrList list, cudaStream_t stream,
                                   const SlabRef& slab) {
     const int blocks = blocks_for(gt.max_groups, kDensityWarps);
     if (neighbour_counts)
-        k_density_tile<true, kSlab><<<blocks, kDensityWarps * 32, 0, stream>>>(
+        k_density_tile<true, kSlab, kExt><<<blocks, kDensityWarps * 32, 0, stream>>>(
             pos_rho, vel_pres, offsets, c, gt.groups, gt.count, neighbour_counts, list, slab);
     else
-        k_density_tile<false, kSlab><<<blocks, kDensityWarps * 32, 0, stream>>>(
+        k_density_tile<false, kSlab, kExt><<<blocks, kDensityWarps * 32, 0, stream>>>(
             pos_rho, vel_pres, offsets, c, gt.groups, gt.count, nullptr, list, slab);
 }
 
 inline void launch_density_tile(float4* pos_rho, float4* vel_pres, const uint32_t* offsets,
-                                const SphConsts& c, const GroupTable& gt,
+                                const SphConstsExt& c, const GroupTable& gt,
                                 uint32_t* neighbour_counts, NbrList list, cudaStream_t stream,
                                 const SlabRef& slab = SlabRef{}) {
-    if (slab.dyn)
-        launch_density_tile_t<true>(pos_rho, vel_pres, offsets, c, gt, neighbour_counts, list, stream, slab);
+    const bool ext = c.phys != 0u;
+    if (slab.dyn && ext)
+        launch_density_tile_t<true, true>(pos_rho, vel_pres, offsets, c, gt, neighbour_counts, list, stream, slab);
+    else if (slab.dyn)
+        launch_density_tile_t<true, false>(pos_rho, vel_pres, offsets, c, gt, neighbour_counts, list, stream, slab);
+    else if (ext)
+        launch_density_tile_t<false, true>(pos_rho, vel_pres, offsets, c, gt, neighbour_counts, list, stream, slab);
     else
-        launch_density_tile_t<false>(pos_rho, vel_pres, offsets, c, gt, neighbour_counts, list, stream, slab);
+        launch_density_tile_t<false, false>(pos_rho, vel_pres, offsets, c, gt, neighbour_counts, list, stream, slab);
 }
 
-template <bool kSlab>
+template <bool kSlab, bool kExt>
 inline void launch_update_tile_t(const float4* pos_rho, const float4* vel_pres,
-                                 const uint32_t* offsets, const SphConsts& c, const GroupTable& gt,
+                                 const uint32_t* offsets, const SphConstsExt& c, const GroupTable& gt,
                                  float4* pos_out, float4* vel_out, float4* forces, NbrList list,
                                  cudaStream_t stream, float4* aos_out, const SlabRef& slab) {
     const int blocks = blocks_for(gt.max_groups, kUpdateWarps);
     constexpr size_t smem = kUpdateWarps * sizeof(UpdateStage);
     if (smem > 48 * 1024) {  // opt-in size; the attribute is per device, so set it per launch
         if (forces)
-            cudaFuncSetAttribute(k_update_tile<true, kSlab>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_update_tile<true, kSlab, kExt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         else
-            cudaFuncSetAttribute(k_update_tile<false, kSlab>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_update_tile<false, kSlab, kExt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     if (forces)
-        k_update_tile<true, kSlab><<<blocks, kUpdateWarps * 32, smem, stream>>>(
+        k_update_tile<true, kSlab, kExt><<<blocks, kUpdateWarps * 32, smem, stream>>>(
             pos_rho, vel_pres, offsets, c, gt.groups, gt.count, pos_out, vel_out, forces,
             list, aos_out, slab);
     else
-        k_update_tile<false, kSlab><<<blocks, kUpdateWarps * 32, smem, stream>>>(
+        k_update_tile<false, kSlab, kExt><<<blocks, kUpdateWarps * 32, smem, stream>>>(
             pos_rho, vel_pres, offsets, c, gt.groups, gt.count, pos_out, vel_out, nullptr,
             list, aos_out, slab);
 }
 
 inline void launch_update_tile(const float4* pos_rho, const float4* vel_pres,
-                               const uint32_t* offsets, const SphConsts& c, const GroupTable& gt,
+                               const uint32_t* offsets, const SphConstsExt& c, const GroupTable& gt,
                                float4* pos_out, float4* vel_out, float4* forces, NbrList list,
                                cudaStream_t stream, float4* aos_out = nullptr,
                                const SlabRef& slab = SlabRef{}) {
-    if (slab.dyn)
-        launch_update_tile_t<true>(pos_rho, vel_pres, offsets, c, gt, pos_out, vel_out, forces, list, stream, aos_out, slab);
+    const bool ext = c.phys != 0u;
+    if (slab.dyn && ext)
+        launch_update_tile_t<true, true>(pos_rho, vel_pres, offsets, c, gt, pos_out, vel_out, forces, list, stream, aos_out, slab);
+    else if (slab.dyn)
+        launch_update_tile_t<true, false>(pos_rho, vel_pres, offsets, c, gt, pos_out, vel_out, forces, list, stream, aos_out, slab);
+    else if (ext)
+        launch_update_tile_t<false, true>(pos_rho, vel_pres, offsets, c, gt, pos_out, vel_out, forces, list, stream, aos_out, slab);
     else
-        launch_update_tile_t<false>(pos_rho, vel_pres, offsets, c, gt, pos_out, vel_out, forces, list, stream, aos_out, slab);
+        launch_update_tile_t<false, false>(pos_rho, vel_pres, offsets, c, gt, pos_out, vel_out, forces, list, stream, aos_out, slab);
 }
 
 }  // namespace wc

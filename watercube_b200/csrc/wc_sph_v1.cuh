@@ -31,11 +31,51 @@ __device__ __forceinline__ float wall_density(const SphConsts& c, float x, float
     return d * 4.0f;
 }
 
+// Extended physics, WC_PHYS_WALL_PARTICLES (not in the reference; oracle wall_weight): the
+// density of the wall particles as a function of the distance s to the wall only -- Harada et
+// al.'s "wall weight function", here the closed-form integral of W_poly6 over the half space
+// behind the wall: wall_w * (128/315 - P(s/h)), P(u) = u - 4u^3/3 + 6u^5/5 - 4u^7/7 + u^9/9.
+__device__ __forceinline__ float wall_weight(const SphConstsExt& c, float s) {
+    const float u = __fdiv_rn(s, c.h), u2 = u * u;
+    float P = 1.0f / 9.0f;
+    P = fmaf(P, u2, -4.0f / 7.0f);
+    P = fmaf(P, u2, 6.0f / 5.0f);
+    P = fmaf(P, u2, -4.0f / 3.0f);
+    P = fmaf(P, u2, 1.0f);
+    P = P * u;
+    return c.wall_w * (128.0f / 315.0f - P);
+}
+__device__ __forceinline__ float wall_density_particles(const SphConstsExt& c, float x, float y,
+                                                        float z) {
+    const float hi = c.size - c.h;
+    float d = 0.0f;
+    if (x < c.h) d += wall_weight(c, x); else if (x > hi) d += wall_weight(c, c.size - x);
+    if (y < c.h) d += wall_weight(c, y); else if (y > hi) d += wall_weight(c, c.size - y);
+    if (z < c.h) d += wall_weight(c, z); else if (z > hi) d += wall_weight(c, c.size - z);
+    return d;
+}
+// ... and the push that undoes a penetration of the wall's rest distance: the acceleration
+// wall_acc * (wall_d - s) along the inward normal (oracle wall_push).
+__device__ __forceinline__ float wall_push(const SphConstsExt& c, float x) {
+    if (x < c.wall_d) return (c.wall_d - x) * c.wall_acc;
+    if (x > c.size - c.wall_d) return -((c.wall_d - (c.size - x)) * c.wall_acc);
+    return 0.0f;
+}
+
 // density.comp:126-133: stored density carries the wall term, pressure does not (Q4).
-__device__ __forceinline__ void finish_density(const SphConsts& c, float sum_t3, float x, float y,
-                                               float z, float* rho_store, float* pres) {
+// kExt: the instantiation that knows the extended physics (chosen by c.phys at run time).
+template <bool kExt = false>
+__device__ __forceinline__ void finish_density(const ConstsOf<kExt>& c, float sum_t3, float x,
+                                               float y, float z, float* rho_store, float* pres) {
     const float rho = (c.m * c.poly6C) * sum_t3;
-    *rho_store = rho + wall_density(c, x, y, z);
+    bool done = false;
+    if constexpr (kExt) {
+        if (c.phys & kPhysWall) {
+            *rho_store = rho + wall_density_particles(c, x, y, z);
+            done = true;
+        }
+    }
+    if (!done) *rho_store = rho + wall_density(c, x, y, z);
     const float q = __fdividef(rho, c.rho0);
     *pres = c.P0 + c.k * ((q * q) * q - 1.0f);
 }
@@ -73,16 +113,57 @@ __device__ __forceinline__ void mouse_force(const SphConsts& c, float x, float y
     *fz = (k * ((s * __fdiv_rn(tz, dd)) * c.spikyC)) * 0.00001f;
 }
 
+// Colour-field sums of the surface tension (extended physics), WITHOUT the common factor
+// -6 * poly6C * m: N = sum t^2 r / rho_j, L = sum t (3 h^2 - 7 r^2) / rho_j over 0 < |r| < h
+// (the particle's own term of L is added by integrate()).
+struct ColourField {
+    float Nx = 0, Ny = 0, Nz = 0, L = 0;
+    __device__ __forceinline__ void add(const SphConstsExt& c, float rx, float ry, float rz,
+                                        float d2, float inv_rho_j) {
+        const float t = c.h2 - d2;
+        const float at = inv_rho_j * t, att = at * t;
+        Nx = fmaf(att, rx, Nx), Ny = fmaf(att, ry, Ny), Nz = fmaf(att, rz, Nz);
+        const float l = at * fmaf(-7.0f, d2, c.h2x3);
+        L += (d2 > 0.0f) ? l : 0.0f;
+    }
+};
+
 // update.comp:191-231: external forces, symplectic Euler, speed clamp, box reflection.
 // (Fp, Fv) are the gathered sums; Fv not yet scaled by the viscosity coefficient.
-__device__ __forceinline__ void integrate(const SphConsts& c, float4 pr, float4 vp, float Fpx,
+template <bool kExt = false>
+__device__ __forceinline__ void integrate(const ConstsOf<kExt>& c, float4 pr, float4 vp, float Fpx,
                                           float Fpy, float Fpz, float Fvx, float Fvy, float Fvz,
-                                          float4* pos_out, float4* vel_out, float4* force_out) {
+                                          float4* pos_out, float4* vel_out, float4* force_out,
+                                          const ColourField& cf = ColourField()) {
     float ex = c.g[0] * pr.w, ey = c.g[1] * pr.w, ez = c.g[2] * pr.w;  // update.comp:145 (Q8)
     float mx = 0.0f, my = 0.0f, mz = 0.0f, wx, wy, wz;
     if (c.mouse_hits) mouse_force(c, pr.x, pr.y, pr.z, vp.w, &mx, &my, &mz);
-    wall_forces(c, pr.x, pr.y, pr.z, &wx, &wy, &wz);
-    ex += mx + wx, ey += my + wy, ez += mz + wz;
+    bool walls_done = false, tension_done = false;
+    if constexpr (kExt) {
+        if (c.phys & kPhysWall) {  // as a force density: F / (rho + eps) below is the push
+            const float rho_e = pr.w + 1e-16f;
+            wx = wall_push(c, pr.x) * rho_e, wy = wall_push(c, pr.y) * rho_e,
+            wz = wall_push(c, pr.z) * rho_e;
+            walls_done = true;
+        }
+    }
+    if (!walls_done) wall_forces(c, pr.x, pr.y, pr.z, &wx, &wy, &wz);
+    if constexpr (kExt) {
+        if (c.phys & kPhysTension) {  // F = -sigma * lap(c) * n / |n| at the surface
+            const float nx = c.grad_m * cf.Nx, ny = c.grad_m * cf.Ny, nz = c.grad_m * cf.Nz;
+            // (+ the particle's own term of the Laplacian; its gradient term is zero)
+            const float lap = c.grad_m * (cf.L + __frcp_rn(pr.w) * (c.h2 * c.h2x3));
+            const float len = __fsqrt_rn((nx * nx + ny * ny) + nz * nz);
+            float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+            if (len > c.n_min) {
+                const float f = __fdiv_rn(-c.sigma * lap, len);
+                sx = f * nx, sy = f * ny, sz = f * nz;
+            }
+            ex += (mx + wx) + sx, ey += (my + wy) + sy, ez += (mz + wz) + sz;
+            tension_done = true;
+        }
+    }
+    if (!tension_done) ex += mx + wx, ey += my + wy, ez += mz + wz;
     const float Fx = (Fpx + Fvx * c.mu) + ex;
     const float Fy = (Fpy + Fvy * c.mu) + ey;
     const float Fz = (Fpz + Fvz * c.mu) + ez;
@@ -143,7 +224,7 @@ k_advect(float4* __restrict__ pos_rho, const float4* __restrict__ vel_pres, int 
 template <bool kDebug>
 __global__ void __launch_bounds__(128)
 k_density_v1(float4* pos_rho, float4* __restrict__ vel_pres, const uint32_t* __restrict__ offsets,
-             SphConsts c, uint32_t* __restrict__ neighbour_counts) {
+             SphConstsExt c, uint32_t* __restrict__ neighbour_counts) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= c.n) return;
     const int i = c.first + t;
@@ -173,7 +254,7 @@ k_density_v1(float4* pos_rho, float4* __restrict__ vel_pres, const uint32_t* __r
         }
     }
     float rho, pres;
-    finish_density(c, acc, p.x, p.y, p.z, &rho, &pres);
+    finish_density<true>(c, acc, p.x, p.y, p.z, &rho, &pres);
     // In place like density.comp:135; the gather only reads x,y,z, which do not change.
     reinterpret_cast<float*>(pos_rho)[4 * (size_t)i + 3] = rho;
     reinterpret_cast<float*>(vel_pres)[4 * (size_t)i + 3] = pres;
@@ -183,7 +264,7 @@ k_density_v1(float4* pos_rho, float4* __restrict__ vel_pres, const uint32_t* __r
 template <bool kDebug>
 __global__ void __launch_bounds__(128)
 k_update_v1(const float4* __restrict__ pos_rho, const float4* __restrict__ vel_pres,
-            const uint32_t* __restrict__ offsets, SphConsts c, float4* __restrict__ pos_out,
+            const uint32_t* __restrict__ offsets, SphConstsExt c, float4* __restrict__ pos_out,
             float4* __restrict__ vel_out, float4* __restrict__ forces) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= c.n) return;
@@ -195,6 +276,8 @@ k_update_v1(const float4* __restrict__ pos_rho, const float4* __restrict__ vel_p
               cz = cell_coord(p.z, c.bin, G) - c.zbase;
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, G - 1);
     float Fpx = 0, Fpy = 0, Fpz = 0, Fvx = 0, Fvy = 0, Fvz = 0;
+    ColourField cf;
+    const bool tension = (c.phys & kPhysTension) != 0u;
     for (int dz = -1; dz <= 1; dz++) {
         const int z = cz + dz;
         if (z < 0 || z >= c.Gz) continue;
@@ -210,14 +293,15 @@ k_update_v1(const float4* __restrict__ pos_rho, const float4* __restrict__ vel_p
                 if (d2 < c.T && j != (uint32_t)i) {
                     pair_force(c, rx, ry, rz, d2, v.w, v, q.w, vel_pres[j], Fpx, Fpy, Fpz, Fvx,
                                Fvy, Fvz);
+                    if (tension) cf.add(c, rx, ry, rz, d2, __frcp_rn(q.w));
                 }
             }
         }
     }
     const float kp = -(c.m * c.spikyC), kv = c.m * c.viscC;
     float4 po, vo, fo;
-    integrate(c, p, v, Fpx * kp, Fpy * kp, Fpz * kp, Fvx * kv, Fvy * kv, Fvz * kv, &po, &vo,
-              kDebug ? &fo : nullptr);
+    integrate<true>(c, p, v, Fpx * kp, Fpy * kp, Fpz * kp, Fvx * kv, Fvy * kv, Fvz * kv, &po, &vo,
+                    kDebug ? &fo : nullptr, cf);
     pos_out[t] = po;
     vel_out[t] = vo;
     if (kDebug) forces[t] = fo;

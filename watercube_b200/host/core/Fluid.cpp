@@ -55,6 +55,7 @@ Fluid::Fluid(const std::string& name)
       time_(0.0),
       handle_(nullptr) {
     derived_ = wc_derived();
+    wc_default_physics(&physics_);
 }
 
 Fluid::~Fluid() { destroyHandles(); }
@@ -79,6 +80,40 @@ FluidRef Fluid::position(vec3 p) { position_ = p; return shared_from_this(); }
 FluidRef Fluid::renderMode(int m) { render_mode_ = m; return shared_from_this(); }
 FluidRef Fluid::device(int ordinal) { device_ = ordinal; return shared_from_this(); }
 FluidRef Fluid::devices(int n) { num_devices_ = n < 1 ? 1 : n; return shared_from_this(); }
+
+FluidRef Fluid::wallParticles(bool on, float wall_rest_density) {
+    physics_.flags = on ? (physics_.flags | WC_PHYS_WALL_PARTICLES)
+                        : (physics_.flags & ~WC_PHYS_WALL_PARTICLES);
+    physics_.wall_rest_density = wall_rest_density;
+    applyPhysics();
+    return shared_from_this();
+}
+
+FluidRef Fluid::surfaceTension(float sigma, float threshold) {
+    if (sigma > 0.0f) {
+        physics_.flags |= WC_PHYS_SURFACE_TENSION;
+        physics_.surface_tension = sigma;
+        physics_.surface_threshold = threshold;
+    } else {
+        physics_.flags &= ~WC_PHYS_SURFACE_TENSION;
+    }
+    applyPhysics();
+    return shared_from_this();
+}
+
+FluidRef Fluid::physics(const wc_physics& ph) {
+    physics_ = ph;
+    applyPhysics();
+    return shared_from_this();
+}
+
+void Fluid::applyPhysics() {
+    if (!slabs_.empty()) {
+        for (wc_handle* s : slabs_) util::check(wc_set_physics(s, &physics_));
+    } else if (handle_) {
+        util::check(wc_set_physics(handle_, &physics_));
+    }
+}
 FluidRef Fluid::seed(uint32_t s) { seed_ = s; return shared_from_this(); }
 FluidRef Fluid::viscosityCoefficient(float c) { viscosity_coefficient_ = c; return shared_from_this(); }
 FluidRef Fluid::stiffness(float s) { stiffness_ = s; return shared_from_this(); }
@@ -128,6 +163,7 @@ FluidRef Fluid::setup() {
     if (!user_particles_) generateInitialParticles();
     if (num_devices_ > 1) {
         setupSlabs();
+        applyPhysics();
         sort_.reset();
         steps_ = 0;
         time_ = 0.0;
@@ -145,6 +181,7 @@ FluidRef Fluid::setup() {
     p.device = device_;
     util::check(wc_create(&p, &handle_));         // prepareBuffers + compileShaders
     util::check(wc_get_derived(handle_, &derived_));
+    applyPhysics();
     util::log("bins %d, bin size %f, kernel radius %f, particle mass %f\n", derived_.num_bins,
               derived_.bin_size, derived_.kernel_radius, derived_.particle_mass);  // :211
 
@@ -267,6 +304,10 @@ void Fluid::saveCheckpoint(const std::string& path) {
     const vec3 mo = mouse_ray_.getOrigin(), md = mouse_ray_.getDirection();
     h.mouse_origin[0] = mo.x, h.mouse_origin[1] = mo.y, h.mouse_origin[2] = mo.z;
     h.mouse_dir[0] = md.x, h.mouse_dir[1] = md.y, h.mouse_dir[2] = md.z;
+    h.physics_flags = physics_.flags;
+    h.surface_tension = physics_.surface_tension, h.surface_threshold = physics_.surface_threshold;
+    h.wall_stiffness = physics_.wall_stiffness, h.wall_distance = physics_.wall_distance;
+    h.wall_rest_density = physics_.wall_rest_density;
     util::saveCheckpoint(path, h, util::getParticles(particleBuffer1(), num_particles_));
 }
 
@@ -288,6 +329,14 @@ FluidRef Fluid::restoreCheckpoint(const std::string& path) {
         has_mouse_ray_ = h.has_mouse_ray != 0;
         mouse_ray_ = Ray(vec3(h.mouse_origin[0], h.mouse_origin[1], h.mouse_origin[2]),
                          vec3(h.mouse_dir[0], h.mouse_dir[1], h.mouse_dir[2]));
+        if (h.physics_flags != 0u) {  // (all zero in files written before the record existed)
+            physics_.flags = h.physics_flags;
+            physics_.surface_tension = h.surface_tension, physics_.surface_threshold = h.surface_threshold;
+            physics_.wall_stiffness = h.wall_stiffness, physics_.wall_distance = h.wall_distance;
+            physics_.wall_rest_density = h.wall_rest_density;
+        } else {
+            physics_.flags = 0u;
+        }
     }
     initial_particles_.swap(particles);
     num_particles_ = (int)initial_particles_.size();

@@ -55,6 +55,13 @@ public:
     FluidRef restPressure(float p);
     FluidRef gravityStrength(float g);
     FluidRef gravityDirection(vec3 d);       // what "Rotate Gravity" updates (Fluid.cpp:259-263)
+    // new: the physics the reference's report lists as future work (report.pdf section 6; see
+    // wc_physics in wc_sph.h), off by default = the reference's step.  Before setup() or between
+    // two update() calls; carried by checkpoints.
+    FluidRef wallParticles(bool on, float wall_rest_density = 0.0f);   // Harada et al.'s walls
+    FluidRef surfaceTension(float sigma, float threshold = 7.0f);      // sigma <= 0: off
+    FluidRef physics(const wc_physics& ph);
+    const wc_physics& physics() const { return physics_; }
 
     void setCameraPosition(vec3 p) { camera_position_ = p; }
     void setLightPosition(vec3 p) { light_position_ = p; }
@@ -110,6 +117,7 @@ protected:
     }
     void setupSlabs();   // the decomposed counterpart of setup()'s buffer creation
     void destroyHandles();
+    void applyPhysics();  // physics_ into every handle there is
 
     int num_particles_, grid_res_, render_mode_, device_, num_devices_;
     std::vector<wc_handle*> slabs_;  // z order; handle_ == slabs_[0] when decomposed
@@ -126,6 +134,7 @@ protected:
     SortRef sort_;
     wc_handle* handle_;
     wc_derived derived_;
+    wc_physics physics_;
 };
 
 }  // namespace core

@@ -115,7 +115,10 @@ struct CheckpointHeader {
     float position[3];      // Fluid::position_, which the mouse ray is relative to
     int32_t has_mouse_ray;
     float mouse_origin[3], mouse_dir[3];
-    uint8_t reserved2[24];
+    // ---- the wc_physics record (extended physics).  All zero in files written before it
+    // existed, which reads as "flags 0": the reference's step, the object's values kept.
+    uint32_t physics_flags;
+    float surface_tension, surface_threshold, wall_stiffness, wall_distance, wall_rest_density;
 };
 static_assert(sizeof(CheckpointHeader) == 160, "checkpoint header is 160 bytes");
 constexpr size_t kCheckpointHeaderV1Bytes = 64;

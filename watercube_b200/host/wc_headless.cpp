@@ -6,6 +6,8 @@
 //               [--gpus N]         z-slab decomposition over N devices of this box, driven by this
 //                                  one process and thread (core::Fluid::devices); same results
 //               [--stiffness K] [--viscosity MU] [--rest-density R]   per-step parameters
+//               [--wall-particles [--wall-density RHO]] [--surface-tension SIGMA]
+//                                  the report's future-work physics (wc_physics); off = reference
 //               [--initial-only]   (write the initial lattice to --dump; no device needed)
 //               [--checkpoint file]  write a resumable checkpoint (header + AoS) after the run
 //               [--restore file]     start from a checkpoint instead of the initial lattice
@@ -29,6 +31,8 @@ using namespace core;
 int main(int argc, char** argv) {
     int n = 80000, grid = 21, steps = 100, device = 0, gpus = 1;
     float size = 1.0f, stiffness = -1.0f, viscosity = -1.0f, rest_density = -1.0f;
+    float surface_tension = 0.0f, wall_density = 0.0f;
+    bool wall_particles = false;
     const char* dump = nullptr;
     const char* checkpoint = nullptr;
     const char* restore = nullptr;
@@ -48,6 +52,9 @@ int main(int argc, char** argv) {
         else if (const char* v = next("--stiffness")) stiffness = (float)std::atof(v);
         else if (const char* v = next("--viscosity")) viscosity = (float)std::atof(v);
         else if (const char* v = next("--rest-density")) rest_density = (float)std::atof(v);
+        else if (const char* v = next("--surface-tension")) surface_tension = (float)std::atof(v);
+        else if (const char* v = next("--wall-density")) wall_density = (float)std::atof(v);
+        else if (std::strcmp(argv[i], "--wall-particles") == 0) wall_particles = true;
         else if (const char* v = next("--dump")) dump = v;
         else if (const char* v = next("--checkpoint")) checkpoint = v;
         else if (const char* v = next("--restore")) restore = v;
@@ -59,6 +66,8 @@ int main(int argc, char** argv) {
         if (stiffness >= 0) fluid->stiffness(stiffness);
         if (viscosity >= 0) fluid->viscosityCoefficient(viscosity);
         if (rest_density >= 0) fluid->restDensity(rest_density);
+        if (wall_particles) fluid->wallParticles(true, wall_density);
+        if (surface_tension > 0) fluid->surfaceTension(surface_tension);
         if (initial_only) {
             const std::vector<Particle>& init = fluid->initialParticles();
             FILE* f = dump ? std::fopen(dump, "wb") : nullptr;
