@@ -61,6 +61,10 @@ constexpr int kDensityWarps = WC_DENSITY_WARPS;  // warps (= groups) per block, 
 #ifndef WC_UNIFORM_NW
 #define WC_UNIFORM_NW 1
 #endif
+// 1: the update pass batches the list words strided instead of consecutively (update_group).
+#ifndef WC_STRIDED_BATCHES
+#define WC_STRIDED_BATCHES 1
+#endif
 #ifndef WC_SLAB_MIDDLE_OUT
 #define WC_SLAB_MIDDLE_OUT 1
 #endif
@@ -745,8 +749,32 @@ __device__ __forceinline__ void update_group(const float4* __restrict__ pos_rho,
         const uint32_t* wmask = list.mask + (size_t)x.g * list.cap_words * 32 + lane;
         const uint32_t first_target = (uint32_t)(x.i - lane);
         st.init(lane);
+#if WC_STRIDED_BATCHES
+        // The nw list words go into nb = ceil(nw / K) batches, batch b taking the words b, b + nb,
+        // b + 2 nb, ...: equal-sized batches, each a cross-section of the nine slices.  The walk
+        // ends a batch with the lane that accepted most of it, and consecutive words (one
+        // slice: one side of the group) are accepted unevenly -- tests/model/model_walk.py:
+        // 37.7 instead of 41.0 pair-loop iterations per group.
+        const uint32_t nb = (nw + (uint32_t)kReplayWords - 1u) / (uint32_t)kReplayWords;
+        for (uint32_t b = 0; b < nb; b++) {
+            uint32_t jj[kReplayWords];
+            int nwb = 0;
+#pragma unroll
+            for (int u = 0; u < kReplayWords; u++) {
+                const uint32_t w = b + (uint32_t)u * nb;
+                jj[u] = kNoIndex;
+                uint32_t mk = 0u;
+                if (w < nw) {
+                    jj[u] = widx[(size_t)w * 32];
+                    mk = wmask[(size_t)w * 32];
+                    nwb = u + 1;
+                }
+                st.mask[u * 32 + lane] = mk;
+            }
+#else
         for (uint32_t w0 = 0; w0 < nw; w0 += kReplayWords) {
             uint32_t jj[kReplayWords];
+            const int nwb = (int)min((uint32_t)kReplayWords, nw - w0);
 #pragma unroll
             for (int u = 0; u < kReplayWords; u++) {
                 jj[u] = kNoIndex;
@@ -757,6 +785,7 @@ __device__ __forceinline__ void update_group(const float4* __restrict__ pos_rho,
                 }
                 st.mask[u * 32 + lane] = mk;
             }
+#endif
 #pragma unroll
             for (int u = 0; u < kReplayWords; u++) {
                 if (jj[u] != kNoIndex) {
@@ -777,7 +806,7 @@ __device__ __forceinline__ void update_group(const float4* __restrict__ pos_rho,
             }
             __syncwarp();
 #endif
-            acc.walk(st, (int)min((uint32_t)kReplayWords, nw - w0), c, p, v);
+            acc.walk(st, nwb, c, p, v);
             __syncwarp();
         }
     }
