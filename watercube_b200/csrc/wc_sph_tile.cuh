@@ -61,9 +61,13 @@ constexpr int kDensityWarps = WC_DENSITY_WARPS;  // warps (= groups) per block, 
 #ifndef WC_UNIFORM_NW
 #define WC_UNIFORM_NW 1
 #endif
-// 1: the update pass batches the list words strided instead of consecutively (update_group).
+// 1: the update pass batches the list words strided instead of consecutively (update_group):
+// 1-2 % faster, but a lane then sums its pairs in another order than the no-list path does, so
+// a group's result depends on whether its list overflowed (list capacity is per handle: the
+// bit-identity of z-slabs and whole grid, and of runs with different neighbour_list_words,
+// would become conditional).  Off: tests/test_gpu_parity.py::test_neighbour_list_replay_...
 #ifndef WC_STRIDED_BATCHES
-#define WC_STRIDED_BATCHES 1
+#define WC_STRIDED_BATCHES 0
 #endif
 #ifndef WC_SLAB_MIDDLE_OUT
 #define WC_SLAB_MIDDLE_OUT 1
