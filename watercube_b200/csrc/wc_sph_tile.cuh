@@ -57,7 +57,8 @@ constexpr int kDensityWarps = WC_DENSITY_WARPS;  // warps (= groups) per block, 
 #ifndef WC_DROP_SELF
 #define WC_DROP_SELF 1
 #endif
-// 1: slab mode, the gathers start in the middle of the group table (see group_prologue).
+// 1: the update pass' list word count goes through a shuffle, so that ptxas can see that it
+// is warp-uniform (update_group; without it: convergence checks around the walk, spills).
 #ifndef WC_UNIFORM_NW
 #define WC_UNIFORM_NW 1
 #endif
@@ -69,6 +70,7 @@ constexpr int kDensityWarps = WC_DENSITY_WARPS;  // warps (= groups) per block, 
 #ifndef WC_STRIDED_BATCHES
 #define WC_STRIDED_BATCHES 0
 #endif
+// 1: slab mode, the gathers start in the middle of the group table (see group_prologue).
 #ifndef WC_SLAB_MIDDLE_OUT
 #define WC_SLAB_MIDDLE_OUT 1
 #endif
