@@ -231,6 +231,11 @@ int wc_download_forces(wc_handle* h, float* forces_xyz);
 int wc_upload_sorted(wc_handle* h, const wc_particle* host_aos, int32_t n);
 
 int wc_device_ptrs(wc_handle* h, wc_device_view* view);
+/* The particle count alone (what `numItems` is to Sort, Sort.h:24).  Unlike wc_device_ptrs this
+ * hands out no pointers: wc_device_ptrs lets the caller write buffer 1 behind the library's
+ * back, so after it every sort hashes the positions afresh instead of using the cell counts the
+ * previous update pass prepared. */
+int wc_get_num_particles(wc_handle* h, int32_t* n);
 /* Pack buffer `which` (1 or 2) as 32-byte AoS into a DEVICE buffer (n * 32 bytes). */
 int wc_export_aos_device(wc_handle* h, int32_t which, void* device_dst);
 int wc_sync(wc_handle* h);

@@ -680,3 +680,44 @@ def test_advect_dead_pass_bit_exact(capi, oracle):
         got = fl.download(1)
     ref = oracle.as_f32(oracle.advect(sc.particles, sc.size, f32(FRAME_DT) * f32(0.012)))
     np.testing.assert_array_equal(got, ref)
+
+
+def test_prehash_by_the_update_pass_equals_the_hash_kernel(capi):
+    """Whole-grid handles: the update pass hashes and counts the NEXT step's cells on the
+    positions it has just integrated, and the next sort starts at the scan.  A handle whose raw
+    pointers were handed out (wc_device_ptrs) hashes afresh every step; so does a step after an
+    upload or an advect.  Same bits -- particle buffers and every table of the sort."""
+    sc = scenes.dam_break(120000, seed=23)
+    runs = {}
+    for mode in ("prehash", "ptrs"):
+        with gpu_fluid(capi, sc, capi.FLAG_DEBUG_OUTPUTS | capi.FLAG_STAGE_TIMING) as fl:
+            if mode == "ptrs":
+                fl.view()
+            fl.upload(sc.particles)
+            launches0 = fl.launch_count()
+            for _ in range(6):
+                fl.step(FRAME_DT)
+            per_step = (fl.launch_count() - launches0) / 6.0
+            fl.sort_only()                      # consumes the pre-hash of the last update too
+            runs[mode] = (fl.download(1), fl.download(2), fl.cells(), per_step)
+    a, b = runs["prehash"], runs["ptrs"]
+    for key in ("cell_ids", "counts", "offsets", "perm"):
+        np.testing.assert_array_equal(a[2][key], b[2][key], err_msg=key)
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+    assert a[3] < runs["ptrs"][3]                                    # one launch per step saved
+    # an upload or an advect between two steps: the stale pre-hash must not be used
+    with gpu_fluid(capi, sc, capi.FLAG_DEBUG_OUTPUTS) as fl, \
+            gpu_fluid(capi, sc, capi.FLAG_DEBUG_OUTPUTS) as ref:
+        ref.view()
+        for f in (fl, ref):
+            f.upload(sc.particles)
+            f.step(FRAME_DT)
+            state = f.download(1)
+            state[:, :3] = np.clip(state[:, :3] + f32(0.013), 0.001, sc.size - 0.001)
+            f.upload(state)
+            f.step(FRAME_DT)
+            f.advect_only(FRAME_DT)
+            f.step(FRAME_DT)
+        np.testing.assert_array_equal(fl.download(1), ref.download(1))
+        np.testing.assert_array_equal(fl.cells()["cell_ids"], ref.cells()["cell_ids"])

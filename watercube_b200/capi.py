@@ -34,7 +34,7 @@ EXPORTS = (
     "wc_slab_sort_count", "wc_slab_sync_info", "wc_slab_reorder", "wc_slab_density",
     "wc_slab_update", "wc_advect_only", "wc_slab_ipc_export", "wc_slab_peer_open",
     "wc_slab_peer_attach", "wc_diagnose", "wc_slab_step_peer", "wc_slab_step_peer_host",
-    "wc_default_physics", "wc_set_physics", "wc_get_physics",
+    "wc_default_physics", "wc_set_physics", "wc_get_physics", "wc_get_num_particles",
 )
 
 
@@ -182,6 +182,7 @@ def lib():
             "wc_default_physics": [C.POINTER(Physics)],
             "wc_set_physics": [vp, C.POINTER(Physics)],
             "wc_get_physics": [vp, C.POINTER(Physics)],
+            "wc_get_num_particles": [vp, C.POINTER(C.c_int32)],
         }
         for name, argtypes in sig.items():
             fn = getattr(L, name)
@@ -294,7 +295,9 @@ class Fluid:
     # -- particle-buffer surface
     @property
     def num_particles(self) -> int:
-        return int(self.view().num_particles)
+        n = C.c_int32()
+        check(lib().wc_get_num_particles(self._h, C.byref(n)))
+        return int(n.value)
 
     def upload(self, particles):
         """util::setParticles into buffer 1.  Accepts ndarray or a raw host pointer + n."""

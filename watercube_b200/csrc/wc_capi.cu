@@ -118,6 +118,16 @@ struct wc_handle {
     // Arena cleared once per sort: counts | scan status | scan tile counter.
     void* arena = nullptr;
     size_t arena_bytes = 0;
+    size_t counts_bytes = 0, status_bytes = 0;  // layout of the arena's head (bind_arena)
+    // Pre-hash (whole grid, tiled kernels): the update pass counts the NEXT sort's cells into a
+    // second arena -- and writes its cell ids / arrival ranks into second arrays -- on the
+    // positions it has just integrated; if buffer 1 is still what the update stored when the
+    // next sort starts, that sort swaps the sets in and begins at the scan.
+    void* arena_next = nullptr;
+    uint32_t* cell_ids_next = nullptr;
+    uint32_t* ranks_next = nullptr;
+    bool prehash_valid = false;   // arena_next / *_next describe buffer 1 as it is now
+    bool prehash_off = false;     // raw device pointers were handed out (wc_device_ptrs)
     uint32_t* counts = nullptr;
     unsigned long long* scan_status = nullptr;
     unsigned int* scan_counter = nullptr;
@@ -185,6 +195,16 @@ enum { kSigLc = 0, kSigHaloPos = 1, kSigHaloRho = 2, kSigMig = 3, kSigPhases = 4
 namespace {
 
 using namespace wc;
+
+// The pointers into the head of the (current) arena.
+void bind_arena(wc_handle* h) {
+    char* a = (char*)h->arena;
+    h->counts = (uint32_t*)a;
+    h->scan_status = (unsigned long long*)(a + h->counts_bytes);
+    h->scan_counter = (unsigned int*)(a + h->counts_bytes + h->status_bytes);
+    h->num_groups = (uint32_t*)(a + h->counts_bytes + h->status_bytes + 128);
+    h->big_count = (uint32_t*)(a + h->counts_bytes + h->status_bytes + 192);
+}
 
 SphConstsExt make_consts(const wc_handle* h, const wc_step_params& sp, float frame_dt) {
     SphConstsExt c;
@@ -335,6 +355,21 @@ int sort_count_phase(wc_handle* h, bool timed) {
     const float bin = h->d.bin_size;
     int rc;
     if (timed && (rc = record(h, 0))) return rc;
+    if (h->prehash_valid) {
+        // the update pass of the previous step already hashed and counted its output
+        // (PreHash, wc_sph_tile.cuh): swap its arena and arrays in, go straight to the scan
+        h->prehash_valid = false;
+        std::swap(h->arena, h->arena_next);
+        std::swap(h->cell_ids, h->cell_ids_next);
+        std::swap(h->ranks, h->ranks_next);
+        bind_arena(h);
+        if (timed && (rc = record(h, 1))) return rc;
+        k_scan<<<div_up(h->num_bins, kScanTile), kScanThreads, 0, h->stream>>>(
+            h->counts, h->offsets, h->num_bins, h->scan_status, h->scan_counter, 0u);
+        WC_CHECK_LAUNCH(h);
+        if (timed && (rc = record(h, 2))) return rc;
+        return WC_OK;
+    }
     // clearCountBuffer (Sort.cpp:255) -- one memset also resets the scan bookkeeping.
     WC_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
     if (!h->slab) {
@@ -473,7 +508,8 @@ int run_density(wc_handle* h, const wc_step_params& sp) {
 }
 
 int run_update(wc_handle* h, const wc_step_params& sp, float frame_dt,
-               float4* aos_out = nullptr) {
+               float4* aos_out = nullptr, bool prehash = true) {
+    h->prehash_valid = false;  // buffer 1 is about to change
     if (!h->slab && h->n == 0) return WC_OK;
     const SphConstsExt c = make_consts(h, sp, frame_dt);
     const bool dbg = h->p.flags & WC_FLAG_DEBUG_OUTPUTS;
@@ -482,10 +518,17 @@ int run_update(wc_handle* h, const wc_step_params& sp, float frame_dt,
                              ? NbrList{h->nbr_idx, h->nbr_mask, h->nbr_words, h->nbr_cap_words}
                              : NbrList{nullptr, nullptr, nullptr, 0};
     const bool simple = h->p.flags & WC_FLAG_SIMPLE_KERNELS;
-    if (!simple)
+    if (!simple) {
+        PreHash pre{nullptr, nullptr, nullptr};
+        if (prehash && h->arena_next && !h->prehash_off) {
+            WC_CUDA(cudaMemsetAsync(h->arena_next, 0, h->arena_bytes, h->stream));
+            pre = PreHash{(uint32_t*)h->arena_next, h->cell_ids_next, h->ranks_next};
+        }
         launch_update_tile(h->pos[1], h->vel[1], h->offsets, c, group_table(h), h->pos[0] + h->M,
                            h->vel[0] + h->M, dbg ? h->forces : nullptr, list, h->stream, aos_out,
-                           slab_ref(h, kSigHaloRho));
+                           slab_ref(h, kSigHaloRho), pre);
+        h->prehash_valid = pre.counts != nullptr;
+    }
     if (simple) {
         if (dbg)
             k_update_v1<true><<<div_up(h->n, 128), 128, 0, h->stream>>>(
@@ -839,11 +882,14 @@ int wc_create(const wc_params* p, wc_handle** out) {
         WC_ALLOC(h->neighbour_counts, capz * sizeof(uint32_t));
         WC_ALLOC(h->forces, capz * sizeof(float4));
     }
-    h->counts = (uint32_t*)h->arena;
-    h->scan_status = (unsigned long long*)((char*)h->arena + counts_bytes);
-    h->scan_counter = (unsigned int*)((char*)h->arena + counts_bytes + status_bytes);
-    h->num_groups = (uint32_t*)((char*)h->arena + counts_bytes + status_bytes + 128);
-    h->big_count = (uint32_t*)((char*)h->arena + counts_bytes + status_bytes + 192);
+    h->counts_bytes = counts_bytes;
+    h->status_bytes = status_bytes;
+    bind_arena(h);
+    if (!slab && !(p->flags & WC_FLAG_SIMPLE_KERNELS)) {  // the pre-hash set (see wc_handle)
+        WC_ALLOC(h->arena_next, h->arena_bytes);
+        WC_ALLOC(h->cell_ids_next, in_slots * sizeof(uint32_t));
+        WC_ALLOC(h->ranks_next, in_slots * sizeof(uint32_t));
+    }
     if (slab) {
         size_t off = x_off0;
         for (int k = 0; k < 4; k++) {
@@ -921,6 +967,9 @@ int wc_destroy(wc_handle* h) {
     cudaFree(h->big_cells);
     cudaFree(h->offsets);
     cudaFree(h->arena);
+    cudaFree(h->arena_next);
+    cudaFree(h->cell_ids_next);
+    cudaFree(h->ranks_next);
     cudaFree(h->neighbour_counts);
     cudaFree(h->forces);
     cudaFree(h->nbr_idx);
@@ -963,6 +1012,7 @@ static int upload_into(wc_handle* h, int buf, const wc_particle* host_aos, int32
     if (n > h->cap) return fail(WC_ERR_CAPACITY, "n = %d exceeds capacity %d", n, h->cap);
     WC_CUDA(cudaSetDevice(h->p.device));
     h->n = n;
+    if (buf == 0) h->prehash_valid = false;
     if (h->slab) {  // the device record follows: buffer 1's owned count is the next step's input
         const int rcs = slab_sync_host(h);
         if (rcs) return rcs;
@@ -1093,7 +1143,8 @@ int wc_step_host(wc_handle* h, float frame_dt, const wc_step_params* sp,
     if ((rc = run_sort(h, true))) return rc;
     if ((rc = run_density(h, *sp))) return rc;
     if ((rc = record(h, 4))) return rc;
-    if ((rc = run_update(h, *sp, frame_dt, mapped))) return rc;
+    // (no pre-hash: the next call uploads a fresh buffer 1)
+    if ((rc = run_update(h, *sp, frame_dt, mapped, false))) return rc;
     if ((rc = record(h, 5))) return rc;
     h->have_times = (h->p.flags & WC_FLAG_STAGE_TIMING) != 0;
     if (!mapped) return wc_download_particles(h, 1, host_out);
@@ -1138,6 +1189,7 @@ int wc_advect_only(wc_handle* h, float frame_dt) {
     if (h->slab) return fail(WC_ERR_INVALID, "wc_advect_only is not available on slab handles");
     WC_CUDA(cudaSetDevice(h->p.device));
     h->have_times = false;
+    h->prehash_valid = false;
     if (h->n > 0) {
         k_advect<<<div_up(h->n, 256), 256, 0, h->stream>>>(h->pos[0], h->vel[0], h->n, h->p.size,
                                                            frame_dt * h->p.time_scale);
@@ -1203,6 +1255,17 @@ int wc_download_forces(wc_handle* h, float* forces_xyz) {
     return WC_OK;
 }
 
+int wc_get_num_particles(wc_handle* h, int32_t* n) {
+    if (!h || !n) return fail(WC_ERR_INVALID, "NULL argument");
+    if (h->slab) {  // num_particles of a slab handle is device state: refresh the host copy
+        WC_CUDA(cudaSetDevice(h->p.device));
+        int rcs = slab_sync_host(h);
+        if (rcs) return rcs;
+    }
+    *n = h->n;
+    return WC_OK;
+}
+
 int wc_device_ptrs(wc_handle* h, wc_device_view* v) {
     if (!h || !v) return fail(WC_ERR_INVALID, "NULL argument");
     if (h->slab) {  // num_particles of a slab handle is device state: refresh the host copy
@@ -1210,6 +1273,10 @@ int wc_device_ptrs(wc_handle* h, wc_device_view* v) {
         int rcs = slab_sync_host(h);
         if (rcs) return rcs;
     }
+    // The caller may now write buffer 1 behind the library's back: from here on every sort
+    // hashes the positions it finds (no pre-hash by the update pass).
+    h->prehash_off = true;
+    h->prehash_valid = false;
     for (int b = 0; b < 2; b++) {
         v->pos_rho[b] = h->pos[b];
         v->vel_pres[b] = h->vel[b];

@@ -575,6 +575,16 @@ __device__ __forceinline__ void gather_group(const float4* pos_rho, const float4
     }
 }
 
+// Hash + count of the NEXT step's sort, done by the update pass on the positions it has just
+// integrated (count.comp:25-36 on this step's output): the next step then starts at the scan.
+// counts: the next step's (zeroed) cell counters; cell_ids / ranks: per output particle, what
+// k_hash_count would have written.  All null: not wanted.
+struct PreHash {
+    uint32_t* counts;
+    uint32_t* cell_ids;
+    uint32_t* ranks;
+};
+
 // Common prologue: which group this warp owns, its targets and row geometry.
 struct GroupCtx {
     int g;           // group number
@@ -582,6 +592,7 @@ struct GroupCtx {
     int i;           // this lane's particle index in the candidate arrays
     bool active;     // the warp has a group
     bool valid;      // this lane has a target
+    int cnt;         // targets of the group (lanes 0 .. cnt - 1 are valid)
     GroupGeom gg;
 };
 
@@ -610,7 +621,7 @@ __device__ __forceinline__ GroupCtx group_prologue(const float4* pos_rho, const 
     // slab_warp_wait); a block beyond the table must not wrap around into it
     if constexpr (kSlab) x.active = __any_sync(0xffffffffu, x.active && vblock < needed_blocks);
     x.valid = false;
-    x.t = x.i = 0;
+    x.t = x.i = x.cnt = 0;
     *p_out = make_float4(0, 0, 0, 0);
     if (!x.active) return x;
     const int G = c.G;
@@ -618,6 +629,7 @@ __device__ __forceinline__ GroupCtx group_prologue(const float4* pos_rho, const 
     x.gg.ry = (int)(rec.y - (uint32_t)x.gg.rz * (uint32_t)G);
     const int cnt = (int)rec.z;  // >= 1
     x.valid = lane < cnt;
+    x.cnt = cnt;
     x.i = (int)rec.x + lane;
     x.t = x.i - c.first;
     float4 p = make_float4(0, 0, 0, 0);
@@ -731,7 +743,7 @@ __device__ __forceinline__ void update_group(const float4* __restrict__ pos_rho,
                                              float4* __restrict__ forces, const NbrList& list,
                                              float4* __restrict__ aos_out, const SlabRef& slab,
                                              UpdateStage& st, unsigned vblock,
-                                             unsigned needed_blocks) {
+                                             unsigned needed_blocks, const PreHash& pre) {
     const int lane = threadIdx.x & 31;
     float4 p;
     const GroupCtx x = group_prologue<kSlab>(pos_rho, c, groups, num_groups, kUpdateWarps, &p,
@@ -832,6 +844,19 @@ __device__ __forceinline__ void update_group(const float4* __restrict__ pos_rho,
         __stcs(&aos_out[2 * (size_t)x.t], po);
         __stcs(&aos_out[2 * (size_t)x.t + 1], vo);
     }
+    if constexpr (!kSlab) {
+        if (pre.counts) {  // k_hash_count for the next step, on the position just stored
+            const unsigned mine = x.cnt >= 32 ? 0xffffffffu : ((1u << x.cnt) - 1u);
+            const uint32_t cn = cell_index(po.x, po.y, po.z, c.bin, c.G);
+            const unsigned same = __match_any_sync(mine, cn);
+            const int leader = __ffs(same) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&pre.counts[cn], (uint32_t)__popc(same));
+            base = __shfl_sync(same, base, leader);
+            pre.cell_ids[x.t] = cn;
+            pre.ranks[x.t] = base + (uint32_t)__popc(same & ((1u << lane) - 1u));
+        }
+    }
 }
 
 // (slab mode: launch sizing as in k_density_tile)
@@ -842,13 +867,14 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
               const uint4* __restrict__ groups, const uint32_t* __restrict__ num_groups,
               float4* __restrict__ pos_out, float4* __restrict__ vel_out,
               float4* __restrict__ forces, NbrList list, float4* __restrict__ aos_out,
-              SlabRef slab) {
+              SlabRef slab, PreHash pre) {
     extern __shared__ __align__(16) unsigned char s_dyn[];  // kUpdateWarps stages (may exceed 48 KB)
     UpdateStage* s_stage = reinterpret_cast<UpdateStage*>(s_dyn);
     UpdateStage& st = s_stage[threadIdx.x >> 5];
     if constexpr (!kSlab) {
         update_group<kDebug, false, kExt>(pos_rho, vel_pres, offsets, c, groups, num_groups, pos_out,
-                                    vel_out, forces, list, aos_out, slab, st, blockIdx.x, gridDim.x);
+                                    vel_out, forces, list, aos_out, slab, st, blockIdx.x, gridDim.x,
+                                    pre);
     } else {
         // A dead step (sticky error in the slab record) has an empty group table: the arena
         // memset zeroed the count and k_finish_sort did not build one.  (No early exit of the
@@ -856,7 +882,7 @@ k_update_tile(const float4* __restrict__ pos_rho, const float4* __restrict__ vel
         // allocates the walk loop 8 % longer; update_group's own test of the count covers both.)
         const uint32_t blocks = max(1u, (*num_groups + kUpdateWarps - 1u) / kUpdateWarps);
         update_group<kDebug, true, kExt>(pos_rho, vel_pres, offsets, c, groups, num_groups, pos_out,
-                                   vel_out, forces, list, aos_out, slab, st, blockIdx.x, blocks);
+                                   vel_out, forces, list, aos_out, slab, st, blockIdx.x, blocks, pre);
     }
 }
 
@@ -902,7 +928,8 @@ template <bool kSlab, bool kExt>
 inline void launch_update_tile_t(const float4* pos_rho, const float4* vel_pres,
                                  const uint32_t* offsets, const SphConstsExt& c, const GroupTable& gt,
                                  float4* pos_out, float4* vel_out, float4* forces, NbrList list,
-                                 cudaStream_t stream, float4* aos_out, const SlabRef& slab) {
+                                 cudaStream_t stream, float4* aos_out, const SlabRef& slab,
+                                 const PreHash& pre) {
     const int blocks = blocks_for(gt.max_groups, kUpdateWarps);
     constexpr size_t smem = kUpdateWarps * sizeof(UpdateStage);
     if (smem > 48 * 1024) {  // opt-in size; the attribute is per device, so set it per launch
@@ -914,27 +941,27 @@ inline void launch_update_tile_t(const float4* pos_rho, const float4* vel_pres,
     if (forces)
         k_update_tile<true, kSlab, kExt><<<blocks, kUpdateWarps * 32, smem, stream>>>(
             pos_rho, vel_pres, offsets, c, gt.groups, gt.count, pos_out, vel_out, forces,
-            list, aos_out, slab);
+            list, aos_out, slab, pre);
     else
         k_update_tile<false, kSlab, kExt><<<blocks, kUpdateWarps * 32, smem, stream>>>(
             pos_rho, vel_pres, offsets, c, gt.groups, gt.count, pos_out, vel_out, nullptr,
-            list, aos_out, slab);
+            list, aos_out, slab, pre);
 }
 
 inline void launch_update_tile(const float4* pos_rho, const float4* vel_pres,
                                const uint32_t* offsets, const SphConstsExt& c, const GroupTable& gt,
                                float4* pos_out, float4* vel_out, float4* forces, NbrList list,
                                cudaStream_t stream, float4* aos_out = nullptr,
-                               const SlabRef& slab = SlabRef{}) {
+                               const SlabRef& slab = SlabRef{}, const PreHash& pre = PreHash{}) {
     const bool ext = c.phys != 0u;
     if (slab.dyn && ext)
-        launch_update_tile_t<true, true>(pos_rho, vel_pres, offsets, c, gt, pos_out, vel_out, forces, list, stream, aos_out, slab);
+        launch_update_tile_t<true, true>(pos_rho, vel_pres, offsets, c, gt, pos_out, vel_out, forces, list, stream, aos_out, slab, pre);
     else if (slab.dyn)
-        launch_update_tile_t<true, false>(pos_rho, vel_pres, offsets, c, gt, pos_out, vel_out, forces, list, stream, aos_out, slab);
+        launch_update_tile_t<true, false>(pos_rho, vel_pres, offsets, c, gt, pos_out, vel_out, forces, list, stream, aos_out, slab, pre);
     else if (ext)
-        launch_update_tile_t<false, true>(pos_rho, vel_pres, offsets, c, gt, pos_out, vel_out, forces, list, stream, aos_out, slab);
+        launch_update_tile_t<false, true>(pos_rho, vel_pres, offsets, c, gt, pos_out, vel_out, forces, list, stream, aos_out, slab, pre);
     else
-        launch_update_tile_t<false, false>(pos_rho, vel_pres, offsets, c, gt, pos_out, vel_out, forces, list, stream, aos_out, slab);
+        launch_update_tile_t<false, false>(pos_rho, vel_pres, offsets, c, gt, pos_out, vel_out, forces, list, stream, aos_out, slab, pre);
 }
 
 }  // namespace wc

@@ -31,18 +31,18 @@ std::vector<Particle> getParticles(Buffer buffer, int num_items) {
     if (buffer.slabs) {  // decomposed fluid: the slabs in z order
         std::vector<Particle> all;
         for (wc_handle* s : *buffer.slabs) {
-            wc_device_view view;
-            check(wc_device_ptrs(s, &view));  // (waits for the slab's queued steps)
+            int32_t count = 0;
+            check(wc_get_num_particles(s, &count));  // (waits for the slab's queued steps)
             const size_t at = all.size();
-            all.resize(at + (size_t)view.num_particles);
+            all.resize(at + (size_t)count);
             check(wc_download_particles(s, (int)buffer.kind, reinterpret_cast<wc_particle*>(all.data() + at)));
         }
         if (num_items >= 0 && (size_t)num_items < all.size()) all.resize((size_t)num_items);
         return all;
     }
-    wc_device_view view;
-    check(wc_device_ptrs(h, &view));
-    std::vector<Particle> all((size_t)view.num_particles);
+    int32_t count = 0;
+    check(wc_get_num_particles(h, &count));
+    std::vector<Particle> all((size_t)count);
     check(wc_download_particles(h, (int)buffer.kind, reinterpret_cast<wc_particle*>(all.data())));
     if (num_items >= 0 && (size_t)num_items < all.size()) all.resize((size_t)num_items);
     return all;
@@ -67,12 +67,12 @@ std::vector<uint32_t> getUints(Buffer buffer, int num_items) {
     if (buffer.slabs)
         throw Error(WC_ERR_INVALID, "getUints: the cell tables of a decomposed fluid are per slab "
                                     "(Fluid::slabHandles + wc_download_cells)");
-    wc_device_view view;
-    check(wc_device_ptrs(h, &view));
+    int32_t count = 0;
+    check(wc_get_num_particles(h, &count));
     wc_derived d;
     check(wc_get_derived(h, &d));
     const bool per_bin = buffer.kind == BufferKind::Counts || buffer.kind == BufferKind::Offsets;
-    std::vector<uint32_t> out(per_bin ? (size_t)d.num_bins : (size_t)view.num_particles);
+    std::vector<uint32_t> out(per_bin ? (size_t)d.num_bins : (size_t)count);
     uint32_t* p = out.data();
     switch (buffer.kind) {
         case BufferKind::CellIds: check(wc_download_cells(h, p, nullptr, nullptr, nullptr, nullptr)); break;
