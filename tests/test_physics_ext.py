@@ -222,6 +222,38 @@ def test_extended_physics_against_the_oracle(capi, oracle, n, flags, simple):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("simple", [False, True], ids=["tiled", "simple"])
+def test_extended_physics_against_the_golden_fixture(capi, simple):
+    """tests/golden/dam_break_4096_ext.npz (frozen oracle output; does not need the oracle build):
+    integers bit-exact, density / pressure / force / state within the fp32 bounds of
+    tests/test_gpu_parity.py, for the particles the fixture marks as clear of the surface
+    threshold."""
+    import os
+
+    from tests.golden import make_golden
+
+    name = "dam_break_4096_ext"
+    factory, overrides, _ = make_golden.CASES[name]
+    sc = factory()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    phys = {k: v for k, v in overrides.items() if k != "physics_flags"}
+    assert phys == PHYS
+    got = gpu_stages(capi, sc, overrides["physics_flags"], simple)
+    for key in ("cell_ids", "counts", "offsets", "perm", "neighbour_counts"):
+        np.testing.assert_array_equal(got[key], g[key], err_msg=key)
+    assert np.all(np.abs(got["sorted"][:, 3] - g["density"]) <= RTOL_RHO * np.abs(g["density"]))
+    assert np.all(np.abs(got["sorted"][:, 7] - g["pressure"]) <= RTOL_P * (np.abs(g["pressure"]) + 100.0))
+    keep = g["threshold_clear"]
+    assert keep.mean() > 0.99
+    F = g["force"][keep]
+    fn = np.abs(F).max(1)
+    err = np.abs(got["force"][keep] - F).max(1)
+    assert np.all(err <= 1e-5 * fn + 1e-6 * fn.max())                 # SURVEY 7.4's per-particle bound
+    assert np.abs(got["out"][keep, 4:7] - g["out"][keep, 4:7]).max() <= 2e-5 * 50.0
+    assert np.abs(got["out"][keep, :3] - g["out"][keep, :3]).max() <= 2e-6
+
+
+@pytest.mark.gpu
 def test_flags_zero_on_the_gpu_is_the_reference_step(capi):
     sc = scenes.dam_break(50000, seed=2)
     outs = []
