@@ -1,5 +1,6 @@
 """Small scenes for compute-sanitizer (tools/sanitize.sh): the whole-grid step -- including a
-crowded cell (the radix reorder) and a group whose cull over-reads past its slice -- and three
+crowded cell (the radix reorder), a group whose cull over-reads past its slice, the pre-hash
+of the second step and a third step with the extended physics switched on -- and three
 virtual ranks with peer memory attached (remote stores + device-side signals)."""
 import os
 import sys
@@ -20,6 +21,8 @@ if which in ("all", "whole"):
         fl.upload(sc.particles)
         for _ in range(2):
             fl.step(FRAME_DT)
+        fl.set_physics(capi.PHYS_WALL_PARTICLES | capi.PHYS_SURFACE_TENSION)
+        fl.step(FRAME_DT)
         out = fl.download(1)
         fl.diagnose(1)
     assert np.isfinite(out).all()
