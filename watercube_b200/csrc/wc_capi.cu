@@ -119,7 +119,8 @@ struct wc_handle {
     void* arena = nullptr;
     size_t arena_bytes = 0;
     size_t counts_bytes = 0, status_bytes = 0;  // layout of the arena's head (bind_arena)
-    // Pre-hash (whole grid, tiled kernels): the update pass counts the NEXT sort's cells into a
+    size_t x_off0 = 0, xbytes[4] = {};          // ... and of the slab mode's extra scan states
+    // Pre-hash (tiled kernels; whole grid and z-slabs): the update pass counts the NEXT sort's cells into a
     // second arena -- and writes its cell ids / arrival ranks into second arrays -- on the
     // positions it has just integrated; if buffer 1 is still what the update stored when the
     // next sort starts, that sort swaps the sets in and begins at the scan.
@@ -204,6 +205,15 @@ void bind_arena(wc_handle* h) {
     h->scan_counter = (unsigned int*)(a + h->counts_bytes + h->status_bytes);
     h->num_groups = (uint32_t*)(a + h->counts_bytes + h->status_bytes + 128);
     h->big_count = (uint32_t*)(a + h->counts_bytes + h->status_bytes + 192);
+    if (h->slab) {
+        size_t off = h->x_off0;
+        for (int k = 0; k < 4; k++) {
+            h->scan_status_x[k] = (unsigned long long*)(a + off);
+            h->scan_counter_x[k] = (unsigned int*)(a + off + h->xbytes[k] - 256);
+            off += h->xbytes[k];
+        }
+        h->done = (uint32_t*)(a + off);  // 8 block counters, zero at every sort
+    }
 }
 
 SphConstsExt make_consts(const wc_handle* h, const wc_step_params& sp, float frame_dt) {
@@ -355,25 +365,22 @@ int sort_count_phase(wc_handle* h, bool timed) {
     const float bin = h->d.bin_size;
     int rc;
     if (timed && (rc = record(h, 0))) return rc;
-    if (h->prehash_valid) {
-        // the update pass of the previous step already hashed and counted its output
-        // (PreHash, wc_sph_tile.cuh): swap its arena and arrays in, go straight to the scan
-        h->prehash_valid = false;
+    // The update pass of the previous step may already have hashed and counted its output
+    // (PreHash, wc_sph_tile.cuh): then its arena and arrays are swapped in and the step starts at
+    // the scan (slab mode: after hashing only the received migrants).
+    const bool prehashed = h->prehash_valid;
+    h->prehash_valid = false;
+    if (prehashed) {
         std::swap(h->arena, h->arena_next);
         std::swap(h->cell_ids, h->cell_ids_next);
         std::swap(h->ranks, h->ranks_next);
         bind_arena(h);
-        if (timed && (rc = record(h, 1))) return rc;
-        k_scan<<<div_up(h->num_bins, kScanTile), kScanThreads, 0, h->stream>>>(
-            h->counts, h->offsets, h->num_bins, h->scan_status, h->scan_counter, 0u);
-        WC_CHECK_LAUNCH(h);
-        if (timed && (rc = record(h, 2))) return rc;
-        return WC_OK;
+    } else {
+        // clearCountBuffer (Sort.cpp:255) -- one memset also resets the scan bookkeeping.
+        WC_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
     }
-    // clearCountBuffer (Sort.cpp:255) -- one memset also resets the scan bookkeeping.
-    WC_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
     if (!h->slab) {
-        if (h->n > 0) {
+        if (h->n > 0 && !prehashed) {
             k_hash_count<<<div_up(h->n, 256), 256, 0, h->stream>>>(h->pos[0], h->n, bin, G,
                                                                     h->cell_ids, h->ranks,
                                                                     h->counts);
@@ -395,8 +402,10 @@ int sort_count_phase(wc_handle* h, bool timed) {
         h->mig_in[0], h->mig_in[1], M, h->pos[0], h->vel[0],
         slab_ref(h, kSigMig, -1, -1, (long long)h->step_no - 1));
     WC_CHECK_LAUNCH(h);
-    k_hash_count_slab<<<div_up(M + h->cap + M, 256), 256, 0, h->stream>>>(
-        h->pos[0], M, h->dyn, bin, G, h->z_begin, h->z_end, h->cell_ids, h->ranks, h->counts);
+    // (pre-hashed: the owned slots are done, only the two migrant windows remain)
+    k_hash_count_slab<<<div_up(prehashed ? 2 * M : M + h->cap + M, 256), 256, 0, h->stream>>>(
+        h->pos[0], M, h->dyn, bin, G, h->z_begin, h->z_end, h->cell_ids, h->ranks, h->counts,
+        prehashed ? 1 : 0);
     WC_CHECK_LAUNCH(h);
     if (timed && (rc = record(h, 1))) return rc;
     const int owned_bins = (h->Lz - 2) * G2;
@@ -522,7 +531,8 @@ int run_update(wc_handle* h, const wc_step_params& sp, float frame_dt,
         PreHash pre{nullptr, nullptr, nullptr};
         if (prehash && h->arena_next && !h->prehash_off) {
             WC_CUDA(cudaMemsetAsync(h->arena_next, 0, h->arena_bytes, h->stream));
-            pre = PreHash{(uint32_t*)h->arena_next, h->cell_ids_next, h->ranks_next};
+            // (indices of buffer 1's virtual array: the owned region starts at slot M)
+            pre = PreHash{(uint32_t*)h->arena_next, h->cell_ids_next + h->M, h->ranks_next + h->M};
         }
         launch_update_tile(h->pos[1], h->vel[1], h->offsets, c, group_table(h), h->pos[0] + h->M,
                            h->vel[0] + h->M, dbg ? h->forces : nullptr, list, h->stream, aos_out,
@@ -884,20 +894,15 @@ int wc_create(const wc_params* p, wc_handle** out) {
     }
     h->counts_bytes = counts_bytes;
     h->status_bytes = status_bytes;
+    h->x_off0 = x_off0;
+    for (int k = 0; k < 4; k++) h->xbytes[k] = xbytes[k];
     bind_arena(h);
-    if (!slab && !(p->flags & WC_FLAG_SIMPLE_KERNELS)) {  // the pre-hash set (see wc_handle)
+    if (!(p->flags & WC_FLAG_SIMPLE_KERNELS)) {  // the pre-hash set (see wc_handle)
         WC_ALLOC(h->arena_next, h->arena_bytes);
         WC_ALLOC(h->cell_ids_next, in_slots * sizeof(uint32_t));
         WC_ALLOC(h->ranks_next, in_slots * sizeof(uint32_t));
     }
     if (slab) {
-        size_t off = x_off0;
-        for (int k = 0; k < 4; k++) {
-            h->scan_status_x[k] = (unsigned long long*)((char*)h->arena + off);
-            h->scan_counter_x[k] = (unsigned int*)((char*)h->arena + off + xbytes[k] - 256);
-            off += xbytes[k];
-        }
-        h->done = (uint32_t*)((char*)h->arena + off);  // 8 block counters, zero at every sort
         h->mig_bytes = (size_t)(kMigHeaderFloat4 + 2 * (size_t)h->M) * sizeof(float4);
         h->lc_bytes = (kLcHeader + G2) * sizeof(uint32_t);
         for (int k = 0; k < 2; k++) {

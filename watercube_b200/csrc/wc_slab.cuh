@@ -53,13 +53,19 @@ k_slab_begin(const float4* __restrict__ msg_below, const float4* __restrict__ ms
 // count.comp:25-36 over the virtual input [from-below | owned | from-above].  A slot takes
 // part when it holds a received migrant, or an owned particle that is still inside the slab
 // (owned particles that left were sent to the neighbour at the end of the previous step).
+// migrants_only: the owned slots were hashed and counted by the previous step's update pass
+// (PreHash); the 2 M threads cover the two migrant windows.
 __global__ void __launch_bounds__(256)
 k_hash_count_slab(const float4* __restrict__ pos, int M, SlabDyn* __restrict__ dyn, float bin,
                   int G, int z_begin, int z_end, uint32_t* __restrict__ cell_ids,
-                  uint32_t* __restrict__ ranks, uint32_t* __restrict__ counts) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                  uint32_t* __restrict__ ranks, uint32_t* __restrict__ counts, int migrants_only) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_old = (int)dyn->n_in_old;
-    const bool active = i < M + n_old + M;
+    bool active = i < M + n_old + M;
+    if (migrants_only) {
+        active = i < 2 * M;
+        if (i >= M) i += n_old;  // the window behind the owned region
+    }
     uint32_t c = 0xFFFFFFFFu;
     if (active) {
         const bool own = i >= M && i < M + n_old;

@@ -844,16 +844,25 @@ __device__ __forceinline__ void update_group(const float4* __restrict__ pos_rho,
         __stcs(&aos_out[2 * (size_t)x.t], po);
         __stcs(&aos_out[2 * (size_t)x.t + 1], vo);
     }
-    if constexpr (!kSlab) {
-        if (pre.counts) {  // k_hash_count for the next step, on the position just stored
-            const unsigned mine = x.cnt >= 32 ? 0xffffffffu : ((1u << x.cnt) - 1u);
-            const uint32_t cn = cell_index(po.x, po.y, po.z, c.bin, c.G);
-            const unsigned same = __match_any_sync(mine, cn);
+    if (pre.counts) {  // k_hash_count for the next step, on the position just stored
+        const unsigned mine = x.cnt >= 32 ? 0xffffffffu : ((1u << x.cnt) - 1u);
+        uint32_t cn;
+        if constexpr (kSlab) {
+            // a particle that left the slab's layers was packed for the neighbour (k_migrants):
+            // it takes no part in this slab's next sort (k_hash_count_slab)
+            const int cz = cell_coord(po.z, c.bin, c.G) - c.zbase;
+            cn = (cz >= 1 && cz <= c.Gz - 2) ? cell_index(po.x, po.y, po.z, c.bin, c.G, c.zbase)
+                                              : 0xFFFFFFFFu;
+        } else {
+            cn = cell_index(po.x, po.y, po.z, c.bin, c.G);
+        }
+        const unsigned same = __match_any_sync(mine, cn);
+        pre.cell_ids[x.t] = cn;
+        if (cn != 0xFFFFFFFFu) {
             const int leader = __ffs(same) - 1;
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(&pre.counts[cn], (uint32_t)__popc(same));
             base = __shfl_sync(same, base, leader);
-            pre.cell_ids[x.t] = cn;
             pre.ranks[x.t] = base + (uint32_t)__popc(same & ((1u << lane) - 1u));
         }
     }
