@@ -164,10 +164,14 @@ __device__ __forceinline__ void slab_warp_wait(const SlabRef& s, bool below, boo
     const uint32_t* f0 = __any_sync(0xffffffffu, below) ? s.wait[0] : nullptr;
     const uint32_t* f1 = __any_sync(0xffffffffu, above) ? s.wait[1] : nullptr;
     if (!f0 && !f1) return;
+    // The polls are relaxed loads and ONE acquire fence follows: an acquire load is a load plus
+    // an invalidation of the SM's whole L1 (CCTL.IVALL), and __threadfence_system() a
+    // sequentially consistent fence plus another -- three L1 flushes per boundary warp took
+    // the other warps' candidate lines with them (the density pass lives on 52 % L1 hits).
     for (unsigned spins = 0;; spins++) {
         uint32_t v0 = s.step_no, v1 = s.step_no;
-        if (f0) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v0) : "l"(f0) : "memory");
-        if (f1) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v1) : "l"(f1) : "memory");
+        if (f0) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v0) : "l"(f0) : "memory");
+        if (f1) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v1) : "l"(f1) : "memory");
         const bool timed_out = spins > (1u << 26) || (s.dyn->errors & kSlabErrTimeout);
         if (__all_sync(0xffffffffu, (v0 >= s.step_no && v1 >= s.step_no) || timed_out)) {
             if (timed_out && (threadIdx.x & 31) == 0) atomicOr(&s.dyn->errors, kSlabErrTimeout);
@@ -175,7 +179,7 @@ __device__ __forceinline__ void slab_warp_wait(const SlabRef& s, bool below, boo
         }
         __nanosleep(300);
     }
-    __threadfence_system();
+    asm volatile("fence.acq_rel.sys;" ::: "memory");  // pairs with the neighbour's st.release.sys
 }
 
 // Grid-level signal: of the `blocks` blocks that take part, the one that finishes LAST raises
@@ -189,10 +193,19 @@ __device__ __forceinline__ void slab_grid_signal(const SlabRef& s, bool wrote_re
     if (!s.done) return;
     const int any_remote = __syncthreads_or(wrote_remote ? 1 : 0);
     if (threadIdx.x == 0) {
-        if (any_remote) __threadfence_system();  // this block's remote stores (ordered by the barrier) first
-        const uint32_t ticket = atomicAdd(s.done, 1u);
+        // This block's remote stores (ordered by the barrier) before its ticket: a RELEASE at
+        // system scope on the ticket itself.  (__threadfence_system() here is a sequentially
+        // consistent fence plus an invalidation of the SM's L1, paid by every block of the
+        // boundary layers while the other blocks of the SM are in their gather loops.)
+        uint32_t ticket;
+        if (any_remote)
+            asm volatile("atom.release.sys.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(s.done) : "memory");
+        else
+            ticket = atomicAdd(s.done, 1u);
         if (ticket == blocks - 1u) {
-            __threadfence_system();
+            // acquire what the other blocks released (the tickets form one RMW chain), then
+            // publish to the neighbours
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
             if (s.raise[0])
                 asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(s.raise[0]), "r"(s.step_no) : "memory");
             if (s.raise[1])
